@@ -1,0 +1,180 @@
+/*
+ * sdcgym.h - C ABI of libsdcgym.so: the B200 (sm_100a) implementation of sdc-gym's data-parallel hot path.
+ *
+ * The reference (pancetta/sdc-gym) is pure Python and has no FFI boundary of its own; the seam this ABI
+ * replaces is the body of the gym env methods
+ *     SDC_Full_Env.reset / .step            sdc_gym/envs/sdc_env.py:316-332, 209-273   (gym id `sdc-v0`)
+ *     SDC_Step_Env.step                     sdc_gym/envs/sdc_env.py:507-572            (gym id `sdc-v1`)
+ *     SpectralRadiusLoss._get_spectral_radius   dp_playground.py:216-231
+ *     ResidualLoss.take_step                dp_playground.py:247-258
+ * executed for a whole batch ("vector") of independent envs per call.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add; sdc_gym_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *  - Every entry point returns 0 on success, a negative SDCGYM_E* code for argument errors, or a positive
+ *    cudaError_t.  Nothing throws across the ABI.
+ *  - Device-pointer entry points never allocate, free or synchronise: all buffers are caller-owned device
+ *    memory, work is enqueued on the caller's `stream` (a cudaStream_t passed as void*).
+ *  - Host-pointer entry points (sdcgym_pipe_*) own pinned staging, device state and their streams inside an
+ *    opaque handle and return when the results are in the caller's host buffers.
+ *  - Batched env state is stored as planes ("struct of arrays"): plane p of env i lives at base[p*ld + i],
+ *    `ld` >= N is the plane stride in elements.  Complex values are two consecutive planes (re, im).
+ *      lam   : 2 planes            lambda of the running episode
+ *      S     : 4*M planes          u_0.re,u_0.im,...,u_{M-1}.im, r_0.re,...,r_{M-1}.im
+ *                                  (row i of the reference observation (2, M) complex128, transposed)
+ *      resnorm : 1 plane           ||r||_inf of the current state (the next step's `norm_res_old`)
+ *      niter, episodes, rng_ctr    int32 / int32 / uint32 planes
+ *  - All arithmetic is IEEE binary64 and reproduces the reference's numpy/OpenBLAS rounding sequence
+ *    (`blas_variant` selects the OpenBLAS core whose scalar tails are emulated).
+ */
+#ifndef SDCGYM_H
+#define SDCGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDCGYM_ABI_VERSION 1
+#define SDCGYM_MAX_M 9
+
+/* error codes (negative); positive return values are cudaError_t */
+#define SDCGYM_EINVAL (-1)       /* bad argument value */
+#define SDCGYM_EUNSUPPORTED (-2) /* M / prec_type / strategy combination not compiled in */
+#define SDCGYM_ENULL (-3)        /* required pointer is NULL */
+#define SDCGYM_ENOMEM (-4)       /* host-pipe allocation failed */
+
+/* env_kind: which reference env class the step reproduces */
+#define SDCGYM_ENV_FULL 0 /* sdc-v0, SDC_Full_Env: iterate to convergence / max_iters / divergence */
+#define SDCGYM_ENV_STEP 1 /* sdc-v1, SDC_Step_Env: one sweep per step */
+
+/* prec_type: how the action parameterises Q_delta (dp_playground.py:194-207) or a fixed matrix
+ * (prec='LU'|'min'|'EE'|'zeros', sdc_env.py:141-188; the matrix itself is supplied in `Qd_fixed`) */
+#define SDCGYM_PREC_DIAG 0
+#define SDCGYM_PREC_LOWER_DIAG 1
+#define SDCGYM_PREC_LOWER_TRI 2
+#define SDCGYM_PREC_STRICTLY_LOWER_TRI 3
+#define SDCGYM_PREC_FIXED 4
+
+/* reward_strategy (sdc_env.py:427-463) */
+#define SDCGYM_REW_ITERATION_ONLY 0
+#define SDCGYM_REW_RESIDUAL_CHANGE 1
+#define SDCGYM_REW_GAUSS_KERNEL 2
+#define SDCGYM_REW_FAST_CONVERGENCE 3
+#define SDCGYM_REW_SMOOTH_FAST_CONVERGENCE 4
+#define SDCGYM_REW_SMOOTHER_FAST_CONVERGENCE 5
+#define SDCGYM_REW_SPECTRAL_RADIUS 6
+
+/* flags plane written by sdcgym_step (one byte per env) */
+#define SDCGYM_FLAG_DONE 1      /* episode ended (gym `done`; always set for sdc-v0) */
+#define SDCGYM_FLAG_CONVERGED 2 /* ||r|| < restol */
+#define SDCGYM_FLAG_ERR 4       /* NaN/Inf or residual grew > 100x (sdc_env.py:234,241,527,532) */
+
+/* OpenBLAS core whose rounding sequence is reproduced */
+#define SDCGYM_BLAS_SKYLAKEX 0
+#define SDCGYM_BLAS_HASWELL 1
+
+/* Static description of a batch of envs = the reference constructor arguments (sdc_env.py:27-46). */
+typedef struct sdcgym_env_desc {
+    int32_t M;                 /* collocation nodes, 2..SDCGYM_MAX_M */
+    int32_t env_kind;          /* SDCGYM_ENV_* */
+    int32_t prec_type;         /* SDCGYM_PREC_* */
+    int32_t action_is_complex; /* free_action_space: actions are (re, im) pairs */
+    int32_t do_scale;          /* map real actions [-1,1] -> [0,1] (sdc_env.py:125-132) */
+    int32_t max_iters;         /* 50 (sdc_env.py:25) */
+    int32_t reward_strategy;   /* SDCGYM_REW_* */
+    int32_t blas_variant;      /* SDCGYM_BLAS_* */
+    int32_t autoreset;         /* DummyVecEnv semantics: a finished env is reset inside the step */
+    int32_t curriculum;        /* lambda_real_interpolation_interval given (sdc_env.py:287-292) */
+    double dt, restol, step_penalty, residual_weight, norm_factor;
+    double lam_re_lo, lam_re_hi, lam_im_lo, lam_im_hi; /* lambda sampling box */
+    double interp_x0, interp_x1;                       /* curriculum episode interval */
+    uint64_t seed;                                     /* Philox key */
+    int64_t env_offset;                                /* global index of local env 0 (multi-GPU shard) */
+    double Q[SDCGYM_MAX_M * SDCGYM_MAX_M];             /* collocation matrix, row-major M x M (leading entries) */
+    double Qd_fixed[SDCGYM_MAX_M * SDCGYM_MAX_M];      /* SDCGYM_PREC_FIXED: real Q_delta, row-major M x M */
+} sdcgym_env_desc;
+
+/* Device-resident state of N envs (planes, see above). */
+typedef struct sdcgym_state {
+    int64_t N, ld;
+    double* lam;       /* [2][ld] */
+    double* S;         /* [4M][ld] */
+    double* resnorm;   /* [ld] */
+    int32_t* niter;    /* [ld] */
+    int32_t* episodes; /* [ld]  num_episodes (sdc_env.py:81,276) */
+    uint32_t* rng_ctr; /* [ld]  number of lambda draws made so far */
+} sdcgym_state;
+
+/* Per-step inputs/outputs (device pointers; NULL outputs are skipped). */
+typedef struct sdcgym_step_io {
+    const double* action;      /* element (env i, component k): action[i*env_stride + k*comp_stride] (+1 = imag) */
+    int64_t action_env_stride; /* in doubles */
+    int64_t action_comp_stride;
+    double* reward;        /* [N] */
+    uint8_t* flags;        /* [N] SDCGYM_FLAG_* */
+    double* info_residual; /* [N]  info['residual'] */
+    int32_t* info_niter;   /* [N]  info['niter'] */
+    double* info_lam;      /* [2][ld] info['lam'] (the lambda the step ran with) */
+    double* terminal_obs;  /* [4M][ld] state at episode end; written for envs whose DONE flag is set */
+    double* old_states;    /* collect_states: (N, 2M, max_iters) complex128, env-major (reference layout) or NULL */
+} sdcgym_step_io;
+
+int sdcgym_abi_version(void);
+
+/* number of action components for (M, prec_type): M, M-1, M(M+1)/2, M(M-1)/2, 0 */
+int sdcgym_num_actions(int M, int prec_type);
+
+/* 1 if the (M, prec_type) combination has a compiled kernel */
+int sdcgym_supported(int M, int prec_type);
+
+/*
+ * reset (sdc_env.py:316-332) of the envs with mask[i] != 0 (all envs when mask == NULL):
+ * episodes += 1, niter = 0, lambda drawn from the Philox stream (or taken from lam_in[2][ld] when non-NULL),
+ * u = 1, r = u0 - C u, resnorm = ||r||_inf.  With old_states != NULL column 0 is set and the rest zeroed.
+ */
+int sdcgym_reset(const sdcgym_env_desc* desc, const sdcgym_state* st, const double* lam_in, const uint8_t* mask,
+                 double* old_states, void* stream);
+
+/* env.step(action) for all N envs (sdc_env.py:209-273 / 507-572), plus the DummyVecEnv auto-reset when
+ * desc->autoreset != 0. */
+int sdcgym_step(const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* io, void* stream);
+
+/* planes S[4M][ld] -> reference observation layout obs[N][2][M] complex128 (interleaved re, im) and back */
+int sdcgym_export_obs(int M, int64_t N, int64_t ld, const double* S, double* obs, void* stream);
+int sdcgym_import_obs(int M, int64_t N, int64_t ld, const double* obs, double* S, void* stream);
+
+/* recompute resnorm = ||r||_inf from S (after a state injection) */
+int sdcgym_refresh_resnorm(int M, int64_t N, int64_t ld, const double* S, double* resnorm, void* stream);
+
+/*
+ * Spectral radius rho(lam*dt * inv(I - lam*dt*Qd) (Q - Qd)) for N (lambda, Q_delta-parameter) pairs
+ * (dp_playground.py:216-228; sdc_env.py:421-425).  lam: [N] complex128 interleaved.  qd: [N][A] real or
+ * complex (interleaved) parameters in get_qdmat's layout (dp_playground.py:194-207); for SDCGYM_PREC_FIXED
+ * `qd` is ignored and Qd_fixed (real M x M) is used.  rho: [N].
+ * If lam == NULL, lambdas are the nodes of a (grid_re x grid_im) tensor grid over [re_lo,re_hi] x [im_lo,im_hi]
+ * (N = grid_re*grid_im, row-major over re then im, end points included) and qd, if given, has a single row.
+ */
+typedef struct sdcgym_rho_desc {
+    int32_t M, prec_type, qd_is_complex, qd_broadcast;
+    double dt;
+    double Q[SDCGYM_MAX_M * SDCGYM_MAX_M];
+    double Qd_fixed[SDCGYM_MAX_M * SDCGYM_MAX_M];
+    int64_t grid_re, grid_im;
+    double re_lo, re_hi, im_lo, im_hi;
+} sdcgym_rho_desc;
+int sdcgym_spectral_radius(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, double* rho,
+                           void* stream);
+
+/* sum of x[0..N) in fp64 with a fixed (N-independent per block, deterministic) reduction tree -> out[0] */
+int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream);
+
+/* Measured-peak helper: runs a dependent-free DFMA chain kernel and returns its FLOP count; time it with
+ * events on `stream`.  flops_out may be NULL. */
+int sdcgym_fp64_peak_probe(int64_t iters, double* sink, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDCGYM_H */

@@ -1,0 +1,70 @@
+"""sdc_gym_b200 - B200-native (sm_100a) implementation of sdc-gym's data-parallel hot path.
+
+Public surface (mirrors the reference's):
+
+* ``make(envname, num_envs=..., **kwargs)`` / ``SDCVecEnv`` - batched ``sdc-v0`` / ``sdc-v1`` envs with the
+  DummyVecEnv protocol (reference ``sdc_gym/__init__.py:3-13``, ``utils/utils.py:235-315``).
+* ``SpectralRadiusLoss`` / ``ResidualLoss`` - batched forward values of the ``dp_playground.py:186-258`` losses.
+* ``VecNormalize`` - device-side observation / reward normalisation (SB3 semantics).
+* ``collocation_matrix`` - the Gauss-Radau-right Q the reference takes from pySDC.
+
+The compute path is ``libsdcgym.so`` (hand-written CUDA, C ABI in ``include/sdcgym.h``); importing this
+package does not need a GPU, constructing an env does.
+"""
+from .collocation import CollGaussRadauRight, collocation_matrix  # noqa: F401
+from .precond import fixed_preconditioner, num_actions, qdmat_from_output  # noqa: F401
+
+REGISTRY = {
+    # id: (env kind, max_episode_steps)  - sdc_gym/__init__.py:3-13
+    "sdc-v0": ("SDC_Full_Env", 1),
+    "sdc-v1": ("SDC_Step_Env", 50),
+}
+
+__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize",
+           "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY"]
+
+
+def __getattr__(name):
+    # lazy: keep `import sdc_gym_b200` free of torch / CUDA
+    if name == "SDCVecEnv":
+        from .vec_env import SDCVecEnv
+        return SDCVecEnv
+    if name in ("SpectralRadiusLoss", "ResidualLoss"):
+        from . import loss
+        return getattr(loss, name)
+    if name == "VecNormalize":
+        from .vec_normalize import VecNormalize
+        return VecNormalize
+    raise AttributeError(name)
+
+
+def make(envname, num_envs=1, **kwargs):
+    """``gym.make(envname, **kwargs)`` for a whole batch: returns an ``SDCVecEnv`` with ``num_envs`` envs."""
+    if envname not in REGISTRY:
+        raise KeyError(f"unknown env id {envname!r}; registered: {sorted(REGISTRY)}")
+    from .vec_env import SDCVecEnv
+    return SDCVecEnv(envname, num_envs=num_envs, **kwargs)
+
+
+_ENV_ARGS = ("M", "dt", "restol", "lambda_real_interval", "lambda_imag_interval",
+             "lambda_real_interpolation_interval", "norm_factor", "residual_weight", "step_penalty",
+             "reward_iteration_only", "reward_strategy", "collect_states")
+
+
+def make_env(args, num_envs=None, include_norm=False, norm_reward=True, **kwargs):
+    """Drop-in for the reference's ``utils.make_env`` (``utils/utils.py:235-315``): same argument handling
+    (``kwargs`` beat ``args``), returns the batched env, optionally wrapped in the device ``VecNormalize``."""
+    if num_envs is None:
+        num_envs = args.num_envs
+    args_kwargs = {a: kwargs.pop(a, getattr(args, a)) for a in _ENV_ARGS}
+    all_kwargs = {**kwargs, **args_kwargs}
+    if getattr(args, "model_class", None) == "SAC":
+        all_kwargs["use_doubles"] = False
+    seed = all_kwargs.pop("seed", getattr(args, "seed", None))
+    env = make(args.envname, num_envs=num_envs, seed=seed, **all_kwargs)
+    if include_norm:
+        from .vec_normalize import VecNormalize
+        model_kwargs = getattr(args, "model_kwargs", None) or {}
+        extra = {"gamma": model_kwargs["gamma"]} if "gamma" in model_kwargs else {}
+        env = VecNormalize(env, norm_obs=getattr(args, "norm_obs", True), norm_reward=norm_reward, **extra)
+    return env

@@ -1,0 +1,177 @@
+"""ctypes binding of ``libsdcgym.so`` (C ABI declared in ``include/sdcgym.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
+
+MAX_M = 9
+ABI_VERSION = 1
+
+ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
+PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
+REWARD_STRATEGIES = {
+    "iteration_only": 0,
+    "residual_change": 1,
+    "gauss_kernel": 2,
+    "fast_convergence": 3,
+    "smooth_fast_convergence": 4,
+    "smoother_fast_convergence": 5,
+    "spectral_radius": 6,
+}
+FLAG_DONE, FLAG_CONVERGED, FLAG_ERR = 1, 2, 4
+BLAS_SKYLAKEX, BLAS_HASWELL = 0, 1
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class EnvDesc(ctypes.Structure):
+    """struct sdcgym_env_desc"""
+
+    _fields_ = [
+        ("M", ctypes.c_int32),
+        ("env_kind", ctypes.c_int32),
+        ("prec_type", ctypes.c_int32),
+        ("action_is_complex", ctypes.c_int32),
+        ("do_scale", ctypes.c_int32),
+        ("max_iters", ctypes.c_int32),
+        ("reward_strategy", ctypes.c_int32),
+        ("blas_variant", ctypes.c_int32),
+        ("autoreset", ctypes.c_int32),
+        ("curriculum", ctypes.c_int32),
+        ("dt", ctypes.c_double),
+        ("restol", ctypes.c_double),
+        ("step_penalty", ctypes.c_double),
+        ("residual_weight", ctypes.c_double),
+        ("norm_factor", ctypes.c_double),
+        ("lam_re_lo", ctypes.c_double),
+        ("lam_re_hi", ctypes.c_double),
+        ("lam_im_lo", ctypes.c_double),
+        ("lam_im_hi", ctypes.c_double),
+        ("interp_x0", ctypes.c_double),
+        ("interp_x1", ctypes.c_double),
+        ("seed", ctypes.c_uint64),
+        ("env_offset", ctypes.c_int64),
+        ("Q", ctypes.c_double * (MAX_M * MAX_M)),
+        ("Qd_fixed", ctypes.c_double * (MAX_M * MAX_M)),
+    ]
+
+
+class State(ctypes.Structure):
+    """struct sdcgym_state (device pointers as integers)"""
+
+    _fields_ = [
+        ("N", ctypes.c_int64),
+        ("ld", ctypes.c_int64),
+        ("lam", ctypes.c_void_p),
+        ("S", ctypes.c_void_p),
+        ("resnorm", ctypes.c_void_p),
+        ("niter", ctypes.c_void_p),
+        ("episodes", ctypes.c_void_p),
+        ("rng_ctr", ctypes.c_void_p),
+    ]
+
+
+class StepIO(ctypes.Structure):
+    """struct sdcgym_step_io"""
+
+    _fields_ = [
+        ("action", ctypes.c_void_p),
+        ("action_env_stride", ctypes.c_int64),
+        ("action_comp_stride", ctypes.c_int64),
+        ("reward", ctypes.c_void_p),
+        ("flags", ctypes.c_void_p),
+        ("info_residual", ctypes.c_void_p),
+        ("info_niter", ctypes.c_void_p),
+        ("info_lam", ctypes.c_void_p),
+        ("terminal_obs", ctypes.c_void_p),
+        ("old_states", ctypes.c_void_p),
+    ]
+
+
+class RhoDesc(ctypes.Structure):
+    """struct sdcgym_rho_desc"""
+
+    _fields_ = [
+        ("M", ctypes.c_int32),
+        ("prec_type", ctypes.c_int32),
+        ("qd_is_complex", ctypes.c_int32),
+        ("qd_broadcast", ctypes.c_int32),
+        ("dt", ctypes.c_double),
+        ("Q", ctypes.c_double * (MAX_M * MAX_M)),
+        ("Qd_fixed", ctypes.c_double * (MAX_M * MAX_M)),
+        ("grid_re", ctypes.c_int64),
+        ("grid_im", ctypes.c_int64),
+        ("re_lo", ctypes.c_double),
+        ("re_hi", ctypes.c_double),
+        ("im_lo", ctypes.c_double),
+        ("im_hi", ctypes.c_double),
+    ]
+
+
+class SdcGymError(RuntimeError):
+    pass
+
+
+_ERRORS = {-1: "SDCGYM_EINVAL (bad argument)", -2: "SDCGYM_EUNSUPPORTED", -3: "SDCGYM_ENULL (null pointer)",
+           -4: "SDCGYM_ENOMEM"}
+
+_lib = None
+
+
+def load():
+    """Load libsdcgym.so; raises if it has not been built (``python -m sdc_gym_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SdcGymError(
+            f"{LIB_PATH} not found: build it with `python -m sdc_gym_b200.build` (needs nvcc). "
+            "There is no CPU fallback for the SDC kernels."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.sdcgym_abi_version.restype = ctypes.c_int
+    if L.sdcgym_abi_version() != ABI_VERSION:
+        raise SdcGymError("libsdcgym.so ABI version mismatch; rebuild")
+    vp, i64, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
+    L.sdcgym_num_actions.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.sdcgym_supported.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.sdcgym_reset.argtypes = [ctypes.POINTER(EnvDesc), ctypes.POINTER(State), vp, vp, vp, vp]
+    L.sdcgym_step.argtypes = [ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(StepIO), vp]
+    L.sdcgym_export_obs.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
+    L.sdcgym_import_obs.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
+    L.sdcgym_refresh_resnorm.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
+    L.sdcgym_sum_f64.argtypes = [i64, vp, vp, vp]
+    L.sdcgym_fp64_peak_probe.argtypes = [i64, vp, _c_double_p, vp]
+    if hasattr(L, "sdcgym_spectral_radius"):
+        L.sdcgym_spectral_radius.argtypes = [ctypes.POINTER(RhoDesc), i64, vp, vp, vp, vp]
+    for name in ("sdcgym_num_actions", "sdcgym_supported", "sdcgym_reset", "sdcgym_step", "sdcgym_export_obs",
+                 "sdcgym_import_obs", "sdcgym_refresh_resnorm", "sdcgym_sum_f64", "sdcgym_fp64_peak_probe",
+                 "sdcgym_spectral_radius"):
+        if hasattr(L, name):
+            getattr(L, name).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise SdcGymError(f"{what}: {_ERRORS.get(rc, rc)}")
+    raise SdcGymError(f"{what}: CUDA error {rc}")
+
+
+def exported_symbols():
+    """Names of all ``sdcgym_*`` entry points declared in include/sdcgym.h (parsed from the header)."""
+    import re
+
+    header = os.path.join(os.path.dirname(_HERE), "include", "sdcgym.h")
+    with open(header) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\bint\s+(sdcgym_[a-z0-9_]+)\s*\(", text)))

@@ -1,0 +1,505 @@
+// step_kernels.cuh - the SDC env kernels: reset, step (sdc-v0 full solve / sdc-v1 single sweep) with fused
+// reward, convergence logic and DummyVecEnv-style auto-reset.  One env per thread; u, r, lambda*dt, the
+// preconditioner inverse and (for small M) the whole system matrix C live in registers; the collocation
+// matrix Q arrives as a __grid_constant__ kernel parameter, i.e. in the constant bank, so every Q entry is
+// an immediate constant operand of the DMUL that uses it.  No shared memory, no memory traffic inside the
+// sweep loop.
+//
+// Reference statements reproduced (sdc_gym/envs/sdc_env.py): reset :306-332, step (sdc-v0) :209-273,
+// step (sdc-v1) :507-572, _scale_action :125-132, _get_prec :134-191, _compute_pinv :193-201, rewards
+// :334-463.  Rounding sequence: SURVEY.md Appendix A / A.2 (exact_math.cuh).
+#pragma once
+#include "../../include/sdcgym.h"
+#include "exact_math.cuh"
+#include "philox.cuh"
+
+namespace sdcgym {
+
+constexpr int kBlock = 128;
+
+template <int M>
+struct StepParams {
+    double Q[M * M];
+    double Qd[M * M];  // fixed real Q_delta (SDCGYM_PREC_FIXED)
+    int64_t N, ld;
+    double* lam;
+    double* S;
+    double* resnorm;
+    int32_t* niter;
+    int32_t* episodes;
+    uint32_t* rng_ctr;
+    const double* action;
+    int64_t a_es, a_cs;
+    double* reward;
+    uint8_t* flags;
+    double* info_res;
+    int32_t* info_niter;
+    double* info_lam;
+    double* term;
+    double* old_states;
+    const double* lam_in;  // reset only
+    const uint8_t* mask;   // reset only
+    double dt, restol, step_penalty, residual_weight, norm_factor;
+    double re_lo, re_hi, im_lo, im_hi, ix0, ix1;
+    uint64_t seed;
+    int64_t env_offset;
+    int32_t prec_type, is_complex, do_scale, max_iters, strategy, autoreset, curriculum;
+};
+
+// ---- C = eye(M) - (lam*dt)*Q, one row (sdc_env.py:302-304; Appendix A step 2).  0 - x is written -x
+//      (differs only in the sign of an exact zero). ----
+template <int M>
+SDCGYM_HD void c_row(const double (&Q)[M * M], double zr, double zi, int i, double (&cr)[M],
+                                      double (&ci)[M]) {
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        double q = Q[i * M + j];
+        cr[j] = (i == j) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
+        ci[j] = -dmul(zi, q);
+    }
+}
+
+// ---- lambda draw (sdc_env.py:282-300): real part first, then imaginary part ----
+template <int M>
+SDCGYM_HD void draw_lambda(const StepParams<M>& p, int64_t i, uint32_t ctr, int32_t episodes,
+                                            double& lr, double& li) {
+    uint64_t g = (uint64_t)(p.env_offset + i);
+    philox4 x = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), ctr, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    double lo = p.re_lo;
+    if (p.curriculum) {
+        // np.interp(num_episodes, interval, reversed(lambda_real_interval))
+        double x0 = p.ix0, x1 = p.ix1, e = (double)episodes;
+        if (e <= x0) lo = p.re_hi;
+        else if (e >= x1) lo = p.re_lo;
+        else {
+            double slope = ddiv(dsub(p.re_lo, p.re_hi), dsub(x1, x0));
+            lo = dadd(dmul(slope, dsub(e, x0)), p.re_hi);
+        }
+    }
+    lr = dadd(lo, dmul(dsub(p.re_hi, lo), u53(x.v[0], x.v[1])));
+    li = dadd(p.im_lo, dmul(dsub(p.im_hi, p.im_lo), u53(x.v[2], x.v[3])));
+}
+
+// ---- initial state of an episode: u = 1, r = u0 - C @ u (sdc_env.py:306-314) ----
+template <int M, int V>
+SDCGYM_HD void initial_state(const double (&Q)[M * M], double zr, double zi, double (&ur)[M],
+                                              double (&ui)[M], double (&rr)[M], double (&ri)[M]) {
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        ur[m] = 1.0;
+        ui[m] = 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        double cr[M], ci[M], yr, yi;
+        c_row<M>(Q, zr, zi, m, cr, ci);
+        zgemv_rowdot<M, V>(cr, ci, ur, ui, yr, yi);
+        rr[m] = dsub(1.0, yr);
+        ri[m] = -yi;
+    }
+}
+
+template <int M>
+SDCGYM_HD void store_state(double* __restrict__ S, int64_t ld, int64_t i, const double (&ur)[M],
+                                            const double (&ui)[M], const double (&rr)[M], const double (&ri)[M]) {
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        S[(2 * m) * ld + i] = ur[m];
+        S[(2 * m + 1) * ld + i] = ui[m];
+        S[(2 * M + 2 * m) * ld + i] = rr[m];
+        S[(2 * M + 2 * m + 1) * ld + i] = ri[m];
+    }
+}
+
+// collect_states buffer (reference layout (2M, max_iters) complex128 per env): write column `col`
+template <int M>
+SDCGYM_HD void store_column(double* __restrict__ os, int64_t e, int max_iters, int col,
+                                             const double (&ur)[M], const double (&ui)[M], const double (&rr)[M],
+                                             const double (&ri)[M]) {
+    double* base = os + (size_t)e * (2 * M) * max_iters * 2;
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        double* pu = base + ((size_t)m * max_iters + col) * 2;
+        double* pr = base + ((size_t)(M + m) * max_iters + col) * 2;
+        pu[0] = ur[m];
+        pu[1] = ui[m];
+        pr[0] = rr[m];
+        pr[1] = ri[m];
+    }
+}
+
+// =====================================================================================================
+// reset kernel
+// =====================================================================================================
+template <int M, int V>
+SDCGYM_HD void reset_one(const StepParams<M>& p, int64_t i) {
+    if (i >= p.N) return;
+    if (p.mask && !p.mask[i]) return;
+    int32_t ep = p.episodes[i] + 1;
+    p.episodes[i] = ep;
+    p.niter[i] = 0;
+    double lr, li;
+    if (p.lam_in) {
+        lr = p.lam_in[i];
+        li = p.lam_in[p.ld + i];
+    } else {
+        uint32_t ctr = p.rng_ctr[i];
+        draw_lambda<M>(p, i, ctr, ep, lr, li);
+        p.rng_ctr[i] = ctr + 1;
+    }
+    p.lam[i] = lr;
+    p.lam[p.ld + i] = li;
+    double zr = dmul(lr, p.dt), zi = dmul(li, p.dt);
+    double ur[M], ui[M], rr[M], ri[M];
+    initial_state<M, V>(p.Q, zr, zi, ur, ui, rr, ri);
+    store_state<M>(p.S, p.ld, i, ur, ui, rr, ri);
+    p.resnorm[i] = inf_norm<M>(rr, ri);
+    if (p.old_states) {
+        store_column<M>(p.old_states, i, p.max_iters, 0, ur, ui, rr, ri);
+        double* base = p.old_states + (size_t)i * (2 * M) * p.max_iters * 2;
+        for (int row = 0; row < 2 * M; row++)
+            for (int c = 1; c < p.max_iters; c++) {
+                base[((size_t)row * p.max_iters + c) * 2] = 0.0;
+                base[((size_t)row * p.max_iters + c) * 2 + 1] = 0.0;
+            }
+    }
+}
+
+// =====================================================================================================
+// rewards (sdc_env.py:334-463), evaluated once per env after the sweeps
+// =====================================================================================================
+template <int M>
+SDCGYM_HD double scaled_inf_norm(const double (&vr)[M], const double (&vi)[M], double nf) {
+    double tr[M], ti[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        tr[m] = dmul(vr[m], nf);  // numpy complex * real scalar
+        ti[m] = dmul(vi[m], nf);
+    }
+    return inf_norm<M>(tr, ti);
+}
+
+template <int M>
+SDCGYM_HD_NOINLINE double reward_func(int strategy, double sp, double rw, double nf, double restol, int max_iters,
+                                           double norm_old_scaled, double norm_init_scaled, const double (&rr)[M],
+                                           const double (&ri)[M], double nr, bool converged, int steps) {
+    switch (strategy) {
+    case SDCGYM_REW_ITERATION_ONLY:
+        return dmul((double)(-steps), sp);
+    case SDCGYM_REW_RESIDUAL_CHANGE: {
+        double b = (nf == 1.0) ? nr : scaled_inf_norm<M>(rr, ri, nf);
+        double rew = fabs(ddiv(dsub(log(norm_old_scaled), log(b)), dsub(log(norm_init_scaled), log(dmul(restol, nf)))));
+        rew = dmul(rew, rw);
+        rew = dsub(rew, dmul((double)steps, sp));
+        return rew;
+    }
+    case SDCGYM_REW_GAUSS_KERNEL: {
+        double ginv = ddiv(1.0, restol);
+        double x = dmul(nr, ginv);
+        double gd = exp(ddiv(-dmul(x, x), 2.0));
+        double extra = 1.0;
+        if (converged) {
+            double k = (double)(max_iters + 1 - steps);
+            extra = dmul(dmul(k, k), 10.0);
+        }
+        return dmul(gd, extra);
+    }
+    case SDCGYM_REW_FAST_CONVERGENCE:
+    case SDCGYM_REW_SMOOTH_FAST_CONVERGENCE:
+    case SDCGYM_REW_SMOOTHER_FAST_CONVERGENCE: {
+        double extra = 1.0;
+        if (converged) {
+            double k = (double)(max_iters + 1 - steps);
+            extra = dmul(dmul(k, k), 10.0);
+        }
+        double rew = (nr == 0.0) ? 1000.0 : -log(nr);
+        if (strategy == SDCGYM_REW_SMOOTH_FAST_CONVERGENCE && rew > 1.0) rew = dadd(1.0, log(rew));
+        rew = dmul(rew, extra);
+        if (strategy == SDCGYM_REW_SMOOTHER_FAST_CONVERGENCE && rew > 1.0) rew = dadd(1.0, log(rew));
+        return rew;
+    }
+    default:
+        return d_nan();
+    }
+}
+
+// Integer-pipe classification thresholds for "is ||r||inf < t ?" / "is ||r||inf > t ?" decisions.
+// With H = absmax_hi(r):  Lmax in [from_hi(H), from_hi(H+1)),  Lmax <= ||r||inf <= 1.4143 * Lmax.
+struct HiBand {
+    int lo;  // H <= lo  =>  ||r||inf <  t   for sure
+    int hi;  // H >= hi  =>  ||r||inf >  t   for sure (and >= t)
+};
+SDCGYM_HD HiBand make_band(double t) {
+    HiBand b;
+    if (!(t >= 0.0) || isinf(t)) {  // NaN / negative / inf threshold: always take the exact path
+        b.lo = -1;
+        b.hi = 0x7fffffff;
+    } else {
+        b.lo = hi_word(ddiv(t, 1.4143)) - 2;
+        b.hi = hi_word(t) + 1;
+    }
+    return b;
+}
+
+// =====================================================================================================
+// step kernel.  KIND: SDCGYM_ENV_FULL / SDCGYM_ENV_STEP.  DENSE: Pinv is a full M x M matrix obtained by
+// the exact np.linalg.inv emulation (any non-diagonal Q_delta), otherwise Pinv is diagonal (prec=None,
+// diag actions).  HOLD: 2 = keep Re and Im of C in registers, 1 = only Re, 0 = recompute z*q on use.
+// =====================================================================================================
+#ifdef __CUDA_ARCH__
+#define SDCGYM_WARP_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define SDCGYM_WARP_ANY(x) (x)
+#endif
+
+template <int M, int KIND, int V, bool DENSE, int HOLD>
+SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
+    const bool valid = tid < p.N;
+    const int64_t i = valid ? tid : p.N - 1;
+    const int64_t ld = p.ld;
+
+    const double lr = p.lam[i], li = p.lam[ld + i];
+    const double zr = dmul(lr, p.dt), zi = dmul(li, p.dt);
+
+    // ---- preconditioner inverse ----
+    constexpr int NP = DENSE ? M * M : M;
+    double Pr[NP], Pi[NP];
+    if (!DENSE) {
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            cplx zq;
+            if (p.is_complex) {
+                cplx d{ld_ro(p.action + i * p.a_es + k * p.a_cs), ld_ro(p.action + i * p.a_es + k * p.a_cs + 1)};
+                zq = cmul_np(cplx{zr, zi}, d);
+            } else {
+                double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                double d = a;
+                if (p.do_scale) d = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
+                zq = cplx{dmul(zr, d), dmul(zi, d)};
+            }
+            cplx inv = crecip<V == 0>(cplx{dsub(1.0, zq.re), -zq.im});
+            Pr[k] = inv.re;
+            Pi[k] = inv.im;
+        }
+    } else {
+        cplx A[M * M], B[M * M];  // column-major work arrays (local memory)
+#pragma unroll 1
+        for (int r = 0, k = 0; r < M; r++)
+#pragma unroll 1
+            for (int c = 0; c < M; c++) {
+                cplx d{0.0, 0.0};
+                bool take;
+                switch (p.prec_type) {
+                case SDCGYM_PREC_LOWER_DIAG: take = (r == c + 1); break;
+                case SDCGYM_PREC_LOWER_TRI: take = (c <= r); break;
+                case SDCGYM_PREC_STRICTLY_LOWER_TRI: take = (c < r); break;
+                case SDCGYM_PREC_DIAG: take = (c == r); break;
+                default: take = false; break;
+                }
+                if (p.prec_type == SDCGYM_PREC_FIXED) {
+                    d.re = p.Qd[r * M + c];
+                } else if (take) {
+                    if (p.is_complex) {
+                        d.re = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                        d.im = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
+                    } else {
+                        double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                        d.re = a;
+                        if (p.do_scale) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
+                    }
+                    k++;
+                }
+                cplx zq = cmul_np(cplx{zr, zi}, d);
+                A[r + c * M] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
+            }
+        cinv_exact<M, V>(A, B);
+#pragma unroll
+        for (int r = 0; r < M; r++)
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                Pr[r * M + c] = B[r + c * M].re;
+                Pi[r * M + c] = B[r + c * M].im;
+            }
+    }
+
+    // ---- system matrix (optionally register resident) ----
+    constexpr int NCR = (HOLD >= 1) ? M * M : 1, NCI = (HOLD >= 2) ? M * M : 1;
+    double Cr[NCR], Ci[NCI];
+    if (HOLD >= 1) {
+#pragma unroll
+        for (int r = 0; r < M; r++)
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                double q = p.Q[r * M + c];
+                Cr[(HOLD >= 1) ? r * M + c : 0] = (r == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
+                if (HOLD >= 2) Ci[(HOLD >= 2) ? r * M + c : 0] = -dmul(zi, q);
+            }
+    }
+
+    // ---- state ----
+    double ur[M], ui[M], rr[M], ri[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        ur[m] = p.S[(2 * m) * ld + i];
+        ui[m] = p.S[(2 * m + 1) * ld + i];
+        rr[m] = p.S[(2 * M + 2 * m) * ld + i];
+        ri[m] = p.S[(2 * M + 2 * m + 1) * ld + i];
+    }
+    const double nr_old = p.resnorm[i];
+    int it = (KIND == SDCGYM_ENV_STEP) ? p.niter[i] : 0;
+
+    // sdc-v1 needs the previous residual for the reward when norm_factor != 1
+    double norm_old_scaled = nr_old;
+    if (KIND == SDCGYM_ENV_STEP && p.strategy == SDCGYM_REW_RESIDUAL_CHANGE && p.norm_factor != 1.0)
+        norm_old_scaled = scaled_inf_norm<M>(rr, ri, p.norm_factor);
+
+    // one sweep: u += Pinv @ r ; r = u0 - C @ u      (sdc_env.py:229-231 / :516-519)
+    auto sweep = [&]() {
+        double dr[M], di[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            if (!DENSE) {
+                diag_rowdot<M, V>(m, Pr[m], Pi[m], rr[m], ri[m], dr[m], di[m]);
+            } else {
+                double ar[M], ai[M];
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    ar[c] = Pr[DENSE ? m * M + c : 0];
+                    ai[c] = Pi[DENSE ? m * M + c : 0];
+                }
+                zgemv_rowdot<M, V>(ar, ai, rr, ri, dr[m], di[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            ur[m] = dadd(ur[m], dr[m]);
+            ui[m] = dadd(ui[m], di[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            double cr[M], ci[M], yr, yi;
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                double q = p.Q[m * M + c];
+                if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1) ? m * M + c : 0];
+                else cr[c] = (m == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
+                if (HOLD >= 2) ci[c] = Ci[(HOLD >= 2) ? m * M + c : 0];
+                else ci[c] = -dmul(zi, q);
+            }
+            zgemv_rowdot<M, V>(cr, ci, ur, ui, yr, yi);
+            rr[m] = dsub(1.0, yr);
+            ri[m] = -yi;
+        }
+    };
+
+    const double thr = dmul(nr_old, 100.0);  // norm_res_old * 100
+    bool conv = false, err = false;
+    double nr = nr_old;
+
+    if (KIND == SDCGYM_ENV_FULL) {
+        // while not done and niter < max_iters  (sdc_env.py:224-247); per-lane early exit by warp vote
+        const HiBand bc = make_band(p.restol), be = make_band(thr);
+        bool act = p.max_iters > 0;
+        bool have_nr = false;
+        while (SDCGYM_WARP_ANY(act)) {
+            if (act) {
+                it++;
+                sweep();
+                const int H = absmax_hi<M>(rr, ri);
+                have_nr = false;
+                if (H >= be.hi) {
+                    err = true;  // NaN / Inf / > 100 x
+                } else if (H > be.lo || (H > bc.lo && H < bc.hi)) {
+                    // inside an ambiguity band: decide on the exact norm, as the reference does
+                    nr = inf_norm<M>(rr, ri);
+                    have_nr = true;
+                    err = isnan(nr) || isinf(nr) || nr > thr;
+                    if (!err) conv = nr < p.restol;
+                } else {
+                    conv = H <= bc.lo;
+                }
+                if (p.old_states && valid && it < p.max_iters) store_column<M>(p.old_states, i, p.max_iters, it, ur, ui, rr, ri);
+                act = !err && !conv && it < p.max_iters;
+            }
+        }
+        if (!have_nr && p.max_iters > 0) nr = inf_norm<M>(rr, ri);
+    } else {
+        sweep();
+        nr = inf_norm<M>(rr, ri);
+        it++;
+        err = isnan(nr) || isinf(nr);
+        err = err || nr > thr;
+        conv = nr < p.restol;
+    }
+
+    // ---- reward ----
+    double rew;
+    if (err) {
+        rew = dmul(-p.step_penalty, (double)(p.max_iters + 1));
+    } else if (p.strategy == SDCGYM_REW_ITERATION_ONLY) {
+        rew = dmul((double)(-it), p.step_penalty);
+    } else {
+        double norm_init_scaled = 0.0;
+        if (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE) {
+            // initial residual of the episode is a function of lambda only: recompute it
+            double tu[M], tv[M], ir[M], ii[M];
+            initial_state<M, V>(p.Q, zr, zi, tu, tv, ir, ii);
+            norm_init_scaled = scaled_inf_norm<M>(ir, ii, p.norm_factor);
+            if (KIND == SDCGYM_ENV_FULL) norm_old_scaled = norm_init_scaled;  // reward_func(initial_residual, ...)
+        }
+        rew = reward_func<M>(p.strategy, p.step_penalty, p.residual_weight, p.norm_factor, p.restol, p.max_iters,
+                             norm_old_scaled, norm_init_scaled, rr, ri, nr, conv, it);
+    }
+
+    const bool done = (KIND == SDCGYM_ENV_FULL) ? true : (conv || it >= p.max_iters || err);
+    if (!valid) return;
+
+    if (p.reward) p.reward[i] = rew;
+    if (p.flags)
+        p.flags[i] = (uint8_t)((done ? SDCGYM_FLAG_DONE : 0) | (conv ? SDCGYM_FLAG_CONVERGED : 0) | (err ? SDCGYM_FLAG_ERR : 0));
+    if (p.info_res) p.info_res[i] = nr;
+    if (p.info_niter) p.info_niter[i] = it;
+    if (p.info_lam) {
+        p.info_lam[i] = lr;
+        p.info_lam[ld + i] = li;
+    }
+    if (KIND == SDCGYM_ENV_STEP && p.old_states && it < p.max_iters)
+        store_column<M>(p.old_states, i, p.max_iters, it, ur, ui, rr, ri);
+
+    if (done && p.term) store_state<M>(p.term, ld, i, ur, ui, rr, ri);
+
+    if (done && p.autoreset) {
+        // DummyVecEnv: obs = env.reset() right after the terminal step
+        int32_t ep = p.episodes[i] + 1;
+        p.episodes[i] = ep;
+        uint32_t ctr = p.rng_ctr[i];
+        double nlr, nli;
+        draw_lambda<M>(p, i, ctr, ep, nlr, nli);
+        p.rng_ctr[i] = ctr + 1;
+        p.lam[i] = nlr;
+        p.lam[ld + i] = nli;
+        const double nzr = dmul(nlr, p.dt), nzi = dmul(nli, p.dt);
+        initial_state<M, V>(p.Q, nzr, nzi, ur, ui, rr, ri);
+        store_state<M>(p.S, ld, i, ur, ui, rr, ri);
+        p.resnorm[i] = inf_norm<M>(rr, ri);
+        p.niter[i] = 0;
+    } else {
+        store_state<M>(p.S, ld, i, ur, ui, rr, ri);
+        p.resnorm[i] = nr;
+        p.niter[i] = it;
+    }
+}
+
+#ifdef __CUDACC__
+template <int M, int V>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ StepParams<M> p) {
+    reset_one<M, V>(p, (int64_t)blockIdx.x * kBlock + threadIdx.x);
+}
+
+template <int M, int KIND, int V, bool DENSE, int HOLD>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepParams<M> p) {
+    step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * kBlock + threadIdx.x);
+}
+#endif
+
+}  // namespace sdcgym

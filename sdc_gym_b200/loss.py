@@ -1,0 +1,122 @@
+"""Batched forward values of the ``dp_playground.py`` losses on the device.
+
+``SpectralRadiusLoss(M, dt, prec_type)(lams, outputs)`` mirrors ``dp_playground.py:186-231``: the mean over the
+batch of ``rho(lam*dt * inv(I - lam*dt*Qd) @ (Q - Qd))`` with ``Qd = get_qdmat(output)``.  The reference runs
+``jnp.linalg.inv`` + ``jnp.linalg.eigvals`` per sample on the CPU (it forces JAX onto the CPU because eigvals
+has no GPU kernel, ``dp_playground.py:981-985``); here one thread per sample runs a complex Hessenberg-QR
+(``csrc/specrad.cuh``) - 1e-10 relative agreement with LAPACK is the contract, not bit equality.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .collocation import collocation_matrix
+from .precond import PREC_TYPES, fixed_preconditioner, num_actions
+
+
+class UnknownPrecTypeError(ValueError):
+    pass
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class SpectralRadiusLoss:
+    def __init__(self, M, dt, prec_type="diag", *, prec=None, Q=None, device=None):
+        if prec is None and prec_type not in PREC_TYPES:
+            raise UnknownPrecTypeError(prec_type)
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.SdcGymError("SpectralRadiusLoss needs a CUDA device: there is no CPU fallback")
+        self._L = _lib.load()
+        self.M, self.dt = int(M), float(dt)
+        self.prec = prec
+        self.prec_type = "fixed" if prec is not None else prec_type
+        self.Q = collocation_matrix(self.M) if Q is None else np.ascontiguousarray(Q, dtype=np.float64)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_out = 0 if prec is not None else num_actions(self.M, prec_type)
+        d = _lib.RhoDesc()
+        d.M, d.prec_type, d.dt = self.M, _lib.PREC_TYPES[self.prec_type], self.dt
+        for k, v in enumerate(self.Q.reshape(-1)):
+            d.Q[k] = float(v)
+        if prec is not None:
+            for k, v in enumerate(fixed_preconditioner(prec, self.M, self.Q).reshape(-1)):
+                d.Qd_fixed[k] = float(v)
+        self._desc = d
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _outputs_tensor(self, outputs, B):
+        torch = _torch()
+        if self.prec is not None:
+            return None, 0, 0
+        t = outputs if isinstance(outputs, torch.Tensor) else torch.as_tensor(np.asarray(outputs))
+        t = t.to(self.device)
+        is_c = t.is_complex()
+        t = t.to(torch.complex128 if is_c else torch.float64)
+        if t.dim() == 1:
+            t = t.reshape(1, -1)
+        if t.shape[-1] != self.n_out:
+            raise ValueError(f"outputs must have {self.n_out} components for prec_type={self.prec_type}")
+        broadcast = int(t.shape[0] == 1 and B != 1)
+        if not broadcast and t.shape[0] != B:
+            raise ValueError("outputs and lams disagree on the batch size")
+        t = t.contiguous()
+        return (torch.view_as_real(t).contiguous() if is_c else t), int(is_c), broadcast
+
+    def spectral_radii(self, lams, outputs=None):
+        """rho per sample as a CUDA float64 tensor (B,).  ``lams``: (B,) or (B, 1) complex (numpy or torch)."""
+        torch = _torch()
+        lam = lams if isinstance(lams, torch.Tensor) else torch.as_tensor(np.asarray(lams, dtype=np.complex128))
+        lam = lam.to(self.device).to(torch.complex128).reshape(-1).contiguous()
+        B = lam.numel()
+        qd, is_c, bc = self._outputs_tensor(outputs, B)
+        d = self._desc
+        d.qd_is_complex, d.qd_broadcast = is_c, bc
+        d.grid_re = d.grid_im = 0
+        rho = torch.empty(B, dtype=torch.float64, device=self.device)
+        lam_r = torch.view_as_real(lam)
+        _lib.check(self._L.sdcgym_spectral_radius(ctypes.byref(d), B, lam_r.data_ptr(),
+                                                  None if qd is None else qd.data_ptr(), rho.data_ptr(),
+                                                  self._stream()), "sdcgym_spectral_radius")
+        self._keep = (lam_r, qd)
+        return rho
+
+    def __call__(self, lams, outputs=None):
+        """mean spectral radius over the batch (``jnp.mean(jax.vmap(...))``, dp_playground.py:230-231)."""
+        rho = self.spectral_radii(lams, outputs)
+        return self.mean(rho)
+
+    def mean(self, rho):
+        torch = _torch()
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.sdcgym_sum_f64(rho.numel(), rho.data_ptr(), out.data_ptr(), self._stream()), "sdcgym_sum_f64")
+        return out[0] / rho.numel()
+
+    def grid(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None):
+        """rho on the (n_re x n_im) tensor grid over the lambda box for ONE Q_delta parameter row (or the fixed
+        ``prec``): lambdas are generated from the grid index on the device (0 bytes in, 8 bytes out per matrix).
+        Returns a CUDA tensor (n_re, n_im)."""
+        torch = _torch()
+        qd, is_c, _ = self._outputs_tensor(output, 1) if self.prec is None else (None, 0, 0)
+        d = self._desc
+        d.qd_is_complex, d.qd_broadcast = is_c, 1
+        d.grid_re, d.grid_im = int(n_re), int(n_im)
+        d.re_lo, d.re_hi = float(lambda_real_interval[0]), float(lambda_real_interval[1])
+        d.im_lo, d.im_hi = float(lambda_imag_interval[0]), float(lambda_imag_interval[1])
+        N = int(n_re) * int(n_im)
+        rho = torch.empty(N, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.sdcgym_spectral_radius(ctypes.byref(d), N, None, None if qd is None else qd.data_ptr(),
+                                                  rho.data_ptr(), self._stream()), "sdcgym_spectral_radius")
+        self._keep = (qd,)
+        return rho.reshape(n_re, n_im)
+
+
+NormLoss = SpectralRadiusLoss  # the reference keeps this alias (dp_playground.py:233)

@@ -1,0 +1,654 @@
+"""``SDCVecEnv`` - the batched, device-resident replacement for
+``DummyVecEnv([lambda: gym.make('sdc-v0'|'sdc-v1', seed=seed+i, **kwargs) for i in range(num_envs)])``
+(reference ``utils/utils.py:284-294`` over ``sdc_gym/envs/sdc_env.py``).
+
+All env state lives in HBM as planes (see ``include/sdcgym.h``); ``reset``/``step`` enqueue hand-written
+sm_100a kernels through the C ABI of ``libsdcgym.so``.  torch is used only for device memory, streams and
+pinned host buffers.  There is no CPU implementation behind this class.
+
+API kept from the reference's callers (``rl_playground.py``, ``dp_playground.py``):
+``reset() -> obs``, ``step(actions) -> (obs, rewards, dones, infos)`` (old-gym 4-tuple, DummyVecEnv
+auto-reset with ``info['terminal_observation']``), ``step_async/step_wait``, ``seed``, ``num_envs``,
+``observation_space``, ``action_space``, ``envs[i].{prec,lam,restol,M,state,initial_residual,num_episodes,
+set_num_episodes}``, ``get_attr/set_attr/env_method``, ``close``.  Constructor keyword names are the
+reference's (``sdc_env.py:27-46``) plus ``prec_type`` (``dp_playground.py:194-207`` layouts).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .collocation import collocation_matrix
+from .precond import fixed_preconditioner, num_actions
+from .spaces import Box
+
+MAX_ITERS = 50  # SDC_Full_Env.max_iters, sdc_env.py:25
+MAX_EPISODE_STEPS = {"sdc-v0": 1, "sdc-v1": 50}  # sdc_gym/__init__.py:3-13
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def detect_blas_variant() -> int:
+    """Which OpenBLAS core the host numpy dispatches to (decides the scalar-tail rounding)."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        for info in threadpool_info():
+            if info.get("internal_api") == "openblas":
+                arch = str(info.get("architecture", "")).lower()
+                if arch in ("haswell", "zen", "sandybridge", "nehalem", "prescott", "core2"):
+                    return _lib.BLAS_HASWELL
+                return _lib.BLAS_SKYLAKEX
+    except Exception:  # pragma: no cover
+        pass
+    return _lib.BLAS_SKYLAKEX
+
+
+class LazyInfos(Sequence):
+    """Sequence of per-env info dicts (``sdc_env.py:265-269,564-568``) materialised on access.
+
+    Array views: ``.niter``, ``.residual``, ``.lam``, ``.done``; ``terminal_observation`` and
+    ``TimeLimit.truncated`` appear for finished envs exactly as DummyVecEnv / TimeLimit add them.
+    """
+
+    def __init__(self, niter, residual, lam, done, truncated_key, terminal_fetch):
+        self.niter, self.residual, self.lam, self.done = niter, residual, lam, done
+        self._truncated_key = truncated_key
+        self._terminal_fetch = terminal_fetch
+        self._terminal = None
+
+    def __len__(self):
+        return len(self.niter)
+
+    def terminal_observations(self):
+        if self._terminal is None:
+            self._terminal = self._terminal_fetch()
+        return self._terminal
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        d = {"residual": self.residual[i], "niter": int(self.niter[i]), "lam": complex(self.lam[i])}
+        if self.done[i]:
+            if self._truncated_key[i]:
+                d["TimeLimit.truncated"] = False
+            d["terminal_observation"] = self.terminal_observations()[i]
+        return d
+
+
+class _EnvProxy:
+    """``vec_env.envs[i]``: attribute view of one env of the batch (reads go through a cached host snapshot)."""
+
+    def __init__(self, vec, i):
+        self._vec, self._i = vec, i
+
+    prec = property(lambda self: self._vec.prec)
+    restol = property(lambda self: self._vec.restol)
+    M = property(lambda self: self._vec.M)
+    dt = property(lambda self: self._vec.dt)
+    Q = property(lambda self: self._vec.Q)
+    max_iters = MAX_ITERS
+    action_space = property(lambda self: self._vec.action_space)
+    observation_space = property(lambda self: self._vec.observation_space)
+
+    @property
+    def lam(self):
+        return complex(self._vec._snapshot()["lam"][self._i])
+
+    @property
+    def state(self):
+        obs = self._vec._snapshot()["obs"][self._i]
+        return (obs[0], obs[1])
+
+    @property
+    def niter(self):
+        return int(self._vec._snapshot()["niter"][self._i])
+
+    @property
+    def num_episodes(self):
+        return int(self._vec._snapshot()["episodes"][self._i])
+
+    @property
+    def initial_residual(self):
+        # a function of lambda only: r0 = u0 - C @ 1 (sdc_env.py:311-313); recomputed on the device
+        return self._vec._initial_residuals()[self._i]
+
+    def set_num_episodes(self, n):
+        self._vec.set_num_episodes(n, indices=[self._i])
+
+
+class _EnvProxies(Sequence):
+    def __init__(self, vec):
+        self._vec = vec
+
+    def __len__(self):
+        return self._vec.num_envs
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return _EnvProxy(self._vec, i)
+
+
+class SDCVecEnv:
+    def __init__(
+        self,
+        envname: str = "sdc-v0",
+        num_envs: int = 1,
+        M: Optional[int] = None,
+        dt: Optional[float] = None,
+        restol: Optional[float] = None,
+        prec: Optional[str] = None,
+        seed: Optional[int] = None,
+        lambda_real_interval=(-100, 0),
+        lambda_imag_interval=(0, 0),
+        lambda_real_interpolation_interval=None,
+        norm_factor=1,
+        residual_weight=0.5,
+        step_penalty=0.1,
+        reward_iteration_only=None,
+        reward_strategy="iteration_only",
+        collect_states=False,
+        use_doubles=True,
+        do_scale=True,
+        free_action_space=False,
+        # ---- extensions over the reference constructor ----
+        prec_type: str = "diag",
+        Q: Optional[np.ndarray] = None,
+        device=None,
+        env_offset: int = 0,
+        blas_variant: Optional[int] = None,
+        autoreset: bool = True,
+        output: str = "numpy",
+        reuse_buffers: bool = False,
+        pipeline_chunks: int = 0,
+    ):
+        torch = _torch()
+        if envname not in _lib.ENV_KINDS:
+            raise ValueError(f"unknown env id {envname!r} (supported: sdc-v0, sdc-v1)")
+        if M is None or dt is None or restol is None:
+            raise TypeError("M, dt and restol are required (as in the reference constructor)")
+        if not torch.cuda.is_available():
+            raise _lib.SdcGymError("SDCVecEnv needs a CUDA device: the SDC kernels have no CPU fallback")
+        if not use_doubles:
+            raise NotImplementedError("use_doubles=False (float32 action space) is not supported; "
+                                      "the kernels compute in fp64 like the reference env")
+        self._L = _lib.load()
+        self.envname = envname
+        self.num_envs = int(num_envs)
+        self.M, self.dt, self.restol = int(M), float(dt), float(restol)
+        self.prec = prec
+        self.prec_type = "fixed" if prec is not None else prec_type
+        if not self._L.sdcgym_supported(self.M, _lib.PREC_TYPES[self.prec_type]):
+            raise NotImplementedError(f"M={self.M}, prec_type={self.prec_type} has no compiled kernel")
+        self.Q = collocation_matrix(self.M) if Q is None else np.ascontiguousarray(Q, dtype=np.float64)
+        self.Qd_fixed = fixed_preconditioner(prec, self.M, self.Q) if prec is not None else np.zeros((self.M, self.M))
+        self.lambda_real_interval = list(lambda_real_interval)
+        self.lambda_imag_interval = list(lambda_imag_interval)
+        self.lambda_real_interpolation_interval = lambda_real_interpolation_interval
+        self.norm_factor, self.residual_weight, self.step_penalty = norm_factor, residual_weight, step_penalty
+        if reward_iteration_only is None:
+            self.reward_strategy = reward_strategy.lower()
+        elif reward_iteration_only:
+            self.reward_strategy = "iteration_only"
+        else:
+            self.reward_strategy = "residual_change"
+        if self.reward_strategy not in _lib.REWARD_STRATEGIES:
+            raise NotImplementedError(f"unknown reward strategy {self.reward_strategy}")
+        self.collect_states = bool(collect_states)
+        self.do_scale = bool(do_scale)
+        self.free_action_space = bool(free_action_space)
+        self.autoreset = bool(autoreset)
+        self.output = output
+        self.reuse_buffers = bool(reuse_buffers)
+        self.max_iters = MAX_ITERS
+        self.n_act = num_actions(self.M, prec_type) if prec is None else self.M
+        self._kernel_n_act = 0 if prec is not None else self.n_act
+
+        # spaces (sdc_env.py:89-110)
+        obs_shape = (self.M * 2, self.max_iters) if collect_states else (2, self.M)
+        self.observation_space = Box(-1e10, 1e10, obs_shape, np.complex128)
+        if free_action_space:
+            self.action_space = Box(-np.inf, np.inf, (self.n_act,), np.complex128)
+        else:
+            self.action_space = Box(-1.0, 1.0, (self.n_act,), np.float64)
+
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        N = self.num_envs
+        self.ld = max(32, (N + 31) // 32 * 32)
+        f64, dev = torch.float64, self.device
+        with torch.cuda.device(self.device):
+            self.lam = torch.zeros((2, self.ld), dtype=f64, device=dev)
+            self.S = torch.zeros((4 * self.M, self.ld), dtype=f64, device=dev)
+            self.resnorm = torch.zeros(self.ld, dtype=f64, device=dev)
+            self.niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
+            self.episodes = torch.zeros(self.ld, dtype=torch.int32, device=dev)
+            self.rng_ctr = torch.zeros(self.ld, dtype=torch.int32, device=dev)
+            self.reward = torch.zeros(self.ld, dtype=f64, device=dev)
+            self.flags = torch.zeros(self.ld, dtype=torch.uint8, device=dev)
+            self.info_residual = torch.zeros(self.ld, dtype=f64, device=dev)
+            self.info_niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
+            self.info_lam = torch.zeros((2, self.ld), dtype=f64, device=dev)
+            self.terminal = torch.zeros((4 * self.M, self.ld), dtype=f64, device=dev)
+            self.obs_aos = torch.zeros((N, 2, self.M, 2), dtype=f64, device=dev)
+            a_w = max(1, self._kernel_n_act) * (2 if free_action_space else 1)
+            self.action_dev = torch.zeros((N, a_w), dtype=f64, device=dev)
+            self.old_states = (torch.zeros((N, 2 * self.M, self.max_iters, 2), dtype=f64, device=dev)
+                               if collect_states else None)
+        self._host = None  # pinned staging, allocated on first numpy-mode step
+        self._snap = None
+        self._init_res = None
+        self._pending = None
+        self._streams = None
+        self.pipeline_chunks = int(pipeline_chunks)
+
+        self._desc = _lib.EnvDesc()
+        d = self._desc
+        d.M, d.env_kind = self.M, _lib.ENV_KINDS[envname]
+        d.prec_type = _lib.PREC_TYPES[self.prec_type]
+        d.action_is_complex, d.do_scale = int(self.free_action_space), int(self.do_scale)
+        d.max_iters = self.max_iters
+        d.reward_strategy = _lib.REWARD_STRATEGIES[self.reward_strategy]
+        d.blas_variant = detect_blas_variant() if blas_variant is None else int(blas_variant)
+        d.autoreset = int(self.autoreset and not self.collect_states)
+        d.curriculum = int(lambda_real_interpolation_interval is not None)
+        d.dt, d.restol = self.dt, self.restol
+        d.step_penalty, d.residual_weight, d.norm_factor = float(step_penalty), float(residual_weight), float(norm_factor)
+        d.lam_re_lo, d.lam_re_hi = float(lambda_real_interval[0]), float(lambda_real_interval[1])
+        d.lam_im_lo, d.lam_im_hi = float(lambda_imag_interval[0]), float(lambda_imag_interval[1])
+        if lambda_real_interpolation_interval is not None:
+            d.interp_x0, d.interp_x1 = (float(v) for v in lambda_real_interpolation_interval)
+        d.seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        d.env_offset = int(env_offset)
+        for k, v in enumerate(self.Q.reshape(-1)):
+            d.Q[k] = float(v)
+        for k, v in enumerate(np.asarray(self.Qd_fixed, dtype=np.float64).reshape(-1)):
+            d.Qd_fixed[k] = float(v)
+        self.blas_variant = d.blas_variant
+        self.envs = _EnvProxies(self)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _state(self, start=0, count=None):
+        count = self.num_envs - start if count is None else count
+        st = _lib.State()
+        st.N, st.ld = count, self.ld
+        st.lam = self.lam.data_ptr() + 8 * start
+        st.S = self.S.data_ptr() + 8 * start
+        st.resnorm = self.resnorm.data_ptr() + 8 * start
+        st.niter = self.niter.data_ptr() + 4 * start
+        st.episodes = self.episodes.data_ptr() + 4 * start
+        st.rng_ctr = self.rng_ctr.data_ptr() + 4 * start
+        return st
+
+    def _desc_for(self, start):
+        if start == 0:
+            return self._desc
+        d = _lib.EnvDesc()
+        ctypes.memmove(ctypes.byref(d), ctypes.byref(self._desc), ctypes.sizeof(d))
+        d.env_offset = self._desc.env_offset + start
+        return d
+
+    def _invalidate(self):
+        self._snap = None
+        self._init_res = None
+
+    # ------------------------------------------------------------------ reset / seed
+    def seed(self, seed=None):
+        """DummyVecEnv.seed: env i gets ``seed + i`` in the reference; here one Philox key for the batch."""
+        self._desc.seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self.rng_ctr.zero_()
+        return [None if seed is None else seed + i for i in range(min(self.num_envs, 64))]
+
+    def set_num_episodes(self, num_episodes, indices=None):
+        if indices is None:
+            self.episodes.fill_(int(num_episodes))
+        else:
+            idx = _torch().as_tensor(list(indices), device=self.device, dtype=_torch().long)
+            self.episodes[idx] = int(num_episodes)
+        self._invalidate()
+
+    def reset(self, lam=None, mask=None):
+        """Reset all envs (or those with ``mask``); ``lam`` (N,) complex injects the lambdas instead of drawing."""
+        torch = _torch()
+        lam_ptr = None
+        if lam is not None:
+            lam_t = torch.as_tensor(np.ascontiguousarray(np.asarray(lam, dtype=np.complex128).reshape(-1)))
+            if lam_t.numel() != self.num_envs:
+                raise ValueError("lam must have one entry per env")
+            lam_planes = torch.zeros((2, self.ld), dtype=torch.float64, device=self.device)
+            ri = torch.view_as_real(lam_t).to(self.device)
+            lam_planes[0, : self.num_envs] = ri[:, 0]
+            lam_planes[1, : self.num_envs] = ri[:, 1]
+            lam_ptr = lam_planes.data_ptr()
+        mask_ptr = None
+        if mask is not None:
+            mask_t = torch.as_tensor(np.asarray(mask, dtype=np.uint8)).to(self.device)
+            mask_ptr = mask_t.data_ptr()
+        st = self._state()
+        os_ptr = self.old_states.data_ptr() if self.old_states is not None else None
+        _lib.check(self._L.sdcgym_reset(ctypes.byref(self._desc), ctypes.byref(st), lam_ptr, mask_ptr, os_ptr,
+                                        self._stream()), "sdcgym_reset")
+        self._invalidate()
+        return self._observation()
+
+    # ------------------------------------------------------------------ observations
+    def _export_obs(self, src, start=0, count=None):
+        count = self.num_envs - start if count is None else count
+        _lib.check(self._L.sdcgym_export_obs(self.M, count, self.ld, src.data_ptr() + 8 * start,
+                                             self.obs_aos.data_ptr() + 8 * start * 4 * self.M, self._stream()),
+                   "sdcgym_export_obs")
+
+    def observation_tensor(self):
+        """Current observation as a CUDA complex128 tensor (N, 2, M) (or (N, 2M, 50) with collect_states)."""
+        torch = _torch()
+        if self.collect_states:
+            return torch.view_as_complex(self.old_states)
+        self._export_obs(self.S)
+        return torch.view_as_complex(self.obs_aos)
+
+    def _observation(self):
+        t = self.observation_tensor()
+        if self.output == "torch":
+            return t
+        return t.cpu().numpy()
+
+    def _snapshot(self):
+        if self._snap is None:
+            torch = _torch()
+            N = self.num_envs
+            self._export_obs(self.S)
+            obs = torch.view_as_complex(self.obs_aos).cpu().numpy()
+            lam = self.lam[:, :N].cpu().numpy()
+            self._snap = dict(obs=obs, lam=lam[0] + 1j * lam[1], niter=self.niter[:N].cpu().numpy(),
+                              episodes=self.episodes[:N].cpu().numpy())
+        return self._snap
+
+    def _initial_residuals(self):
+        if self._init_res is None:
+            # r0 is a function of lambda only: run the reset kernel on scratch planes with lambda injected
+            torch = _torch()
+            N, M = self.num_envs, self.M
+            scratch = dict(lam=torch.empty_like(self.lam), S=torch.empty_like(self.S),
+                           resnorm=torch.empty_like(self.resnorm), niter=torch.empty_like(self.niter),
+                           episodes=torch.zeros_like(self.episodes), rng_ctr=torch.zeros_like(self.rng_ctr))
+            st = _lib.State()
+            st.N, st.ld = N, self.ld
+            for k, t in scratch.items():
+                setattr(st, k, t.data_ptr())
+            _lib.check(self._L.sdcgym_reset(ctypes.byref(self._desc), ctypes.byref(st), self.lam.data_ptr(), None, None,
+                                            self._stream()), "sdcgym_reset")
+            r = scratch["S"][2 * M:, :N].cpu().numpy()
+            self._init_res = (r[0::2] + 1j * r[1::2]).T.copy()
+        return self._init_res
+
+    # ------------------------------------------------------------------ step
+    def _launch_step(self, action_ptr, env_stride, comp_stride, start=0, count=None, want_terminal=True):
+        count = self.num_envs - start if count is None else count
+        io = _lib.StepIO()
+        io.action = action_ptr
+        io.action_env_stride, io.action_comp_stride = env_stride, comp_stride
+        io.reward = self.reward.data_ptr() + 8 * start
+        io.flags = self.flags.data_ptr() + start
+        io.info_residual = self.info_residual.data_ptr() + 8 * start
+        io.info_niter = self.info_niter.data_ptr() + 4 * start
+        io.info_lam = self.info_lam.data_ptr() + 8 * start
+        io.terminal_obs = (self.terminal.data_ptr() + 8 * start) if want_terminal else None
+        io.old_states = (self.old_states.data_ptr() + 8 * start * 2 * self.M * self.max_iters * 2
+                         if self.old_states is not None else None)
+        st = self._state(start, count)
+        d = self._desc_for(start)
+        _lib.check(self._L.sdcgym_step(ctypes.byref(d), ctypes.byref(st), ctypes.byref(io), self._stream()),
+                   "sdcgym_step")
+
+    def step_tensor(self, actions=None, want_terminal=True):
+        """Device-resident step: ``actions`` is a CUDA float64 (N, A) / complex128 (N, A) tensor (ignored for
+        fixed ``prec``).  Nothing is copied to the host and nothing synchronises.  Returns a dict of CUDA
+        tensors (views on the env's own buffers, overwritten by the next step)."""
+        torch = _torch()
+        N = self.num_envs
+        ptr, es, cs = None, 0, 0
+        if self._kernel_n_act > 0:
+            if actions is None:
+                raise ValueError("actions required")
+            if actions.is_complex():
+                if not self.free_action_space:
+                    raise TypeError("complex actions need free_action_space=True")
+                a = torch.view_as_real(actions.to(torch.complex128))
+                es, cs = a.stride(0), a.stride(1)
+            else:
+                if self.free_action_space:
+                    a = torch.view_as_real(actions.to(torch.complex128))
+                    es, cs = a.stride(0), a.stride(1)
+                else:
+                    a = actions.to(torch.float64)
+                    es, cs = a.stride(0), a.stride(1)
+            if a.shape[0] != N or a.shape[1] != self._kernel_n_act:
+                raise ValueError(f"actions must have shape ({N}, {self._kernel_n_act})")
+            self._keep = a
+            ptr = a.data_ptr()
+        self._launch_step(ptr, es, cs, want_terminal=want_terminal)
+        if self.collect_states and self.autoreset:
+            self._reset_done_envs()
+        self._invalidate()
+        return dict(reward=self.reward[:N], flags=self.flags[:N], niter=self.info_niter[:N],
+                    residual=self.info_residual[:N], lam=self.info_lam[:, :N], terminal=self.terminal[:, :N])
+
+    def _reset_done_envs(self):
+        # collect_states: the kernel leaves finished envs alone; snapshot their buffers, then masked reset
+        torch = _torch()
+        N = self.num_envs
+        done = (self.flags[:N] & _lib.FLAG_DONE).to(torch.uint8)
+        self._terminal_old_states = torch.view_as_complex(self.old_states).clone()
+        st = self._state()
+        _lib.check(self._L.sdcgym_reset(ctypes.byref(self._desc), ctypes.byref(st), None, done.data_ptr(),
+                                        self.old_states.data_ptr(), self._stream()), "sdcgym_reset")
+
+    def _ensure_host(self):
+        if self._host is None:
+            torch = _torch()
+            N, M = self.num_envs, self.M
+            pin = dict(pin_memory=True)
+            a_w = self.action_dev.shape[1]
+            self._host = dict(
+                action=torch.zeros((N, a_w), dtype=torch.float64, **pin),
+                obs=torch.zeros((N, 2, M, 2), dtype=torch.float64, **pin),
+                reward=torch.zeros(N, dtype=torch.float64, **pin),
+                flags=torch.zeros(N, dtype=torch.uint8, **pin),
+                niter=torch.zeros(N, dtype=torch.int32, **pin),
+                residual=torch.zeros(N, dtype=torch.float64, **pin),
+                lam=torch.zeros((2, N), dtype=torch.float64, **pin),
+            )
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._host
+
+    def pinned_action_buffer(self):
+        """Page-locked numpy view (N, A) [(N, A) complex128 with free_action_space] that ``step`` uploads
+        from without an intermediate copy: write the actions here and pass this very array to ``step``."""
+        h = self._ensure_host()["action"]
+        a = h.numpy()
+        if self.free_action_space:
+            return a.view(np.complex128)
+        return a
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        actions, self._pending = self._pending, None
+        return self.step(actions)
+
+    def step(self, actions):
+        """(obs, rewards, dones, infos) like ``DummyVecEnv.step`` over the reference envs."""
+        torch = _torch()
+        if self.output == "torch" or (actions is not None and isinstance(actions, torch.Tensor) and actions.is_cuda):
+            out = self.step_tensor(actions if self._kernel_n_act else None)
+            obs = self.observation_tensor()
+            dones = (out["flags"] & _lib.FLAG_DONE).bool()
+            return obs, out["reward"], dones, out
+        N, M = self.num_envs, self.M
+        host = self._ensure_host()
+        # ---- stage actions in pinned memory (no-op when the caller wrote into pinned_action_buffer()) ----
+        if self._kernel_n_act > 0:
+            a = np.asarray(actions)
+            if self.free_action_space:
+                a = np.ascontiguousarray(a, dtype=np.complex128).reshape(N, self._kernel_n_act)
+                stage = host["action"].numpy().view(np.complex128)
+            else:
+                if np.iscomplexobj(a):
+                    raise TypeError("complex actions need free_action_space=True")
+                a = np.asarray(a, dtype=np.float64).reshape(N, self._kernel_n_act)
+                stage = host["action"].numpy()
+            if not np.shares_memory(a, stage):
+                np.copyto(stage, a)
+        if self.collect_states:
+            return self._step_collect_states(host)
+        # ---- chunked pipeline: H2D(actions) | kernel + export | D2H(results) on three streams ----
+        chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(16, N // 65536))
+        bounds = [(N * c // chunks // 32 * 32 if c < chunks else N) for c in range(chunks + 1)]
+        bounds[0] = 0
+        main = torch.cuda.current_stream(self.device)
+        s_in, s_out = self._streams
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        a_w = self.action_dev.shape[1]
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            if hi <= lo:
+                continue
+            if self._kernel_n_act > 0:
+                with torch.cuda.stream(s_in):
+                    self.action_dev[lo:hi].copy_(host["action"][lo:hi], non_blocking=True)
+                main.wait_stream(s_in)
+            self._launch_step(self.action_dev.data_ptr() + 8 * lo * a_w if self._kernel_n_act else None,
+                              a_w, 2 if self.free_action_space else 1, start=lo, count=hi - lo)
+            self._export_obs(self.S, lo, hi - lo)
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                host["obs"][lo:hi].copy_(self.obs_aos[lo:hi], non_blocking=True)
+                host["reward"][lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
+                host["flags"][lo:hi].copy_(self.flags[lo:hi], non_blocking=True)
+                host["niter"][lo:hi].copy_(self.info_niter[lo:hi], non_blocking=True)
+                host["residual"][lo:hi].copy_(self.info_residual[lo:hi], non_blocking=True)
+                host["lam"][:, lo:hi].copy_(self.info_lam[:, lo:hi], non_blocking=True)
+        s_out.synchronize()
+        main.wait_stream(s_out)
+        self._invalidate()
+        return self._host_outputs(host)
+
+    def _host_outputs(self, host):
+        N = self.num_envs
+        cp = (lambda x: x) if self.reuse_buffers else np.copy
+        obs = cp(host["obs"].numpy().view(np.complex128).reshape(N, 2, self.M))
+        rewards = cp(host["reward"].numpy())
+        flags = host["flags"].numpy()
+        dones = (flags & _lib.FLAG_DONE).astype(bool)
+        lam = host["lam"].numpy()
+        niter = cp(host["niter"].numpy())
+        truncated_key = niter >= MAX_EPISODE_STEPS[self.envname] if self.envname == "sdc-v1" else np.ones(N, bool)
+        infos = LazyInfos(niter, cp(host["residual"].numpy()), lam[0] + 1j * lam[1], dones, truncated_key,
+                          self._fetch_terminal)
+        infos.flags = cp(flags)
+        return obs, rewards, dones, infos
+
+    def _fetch_terminal(self):
+        """terminal observations (N, 2, M) complex128 of the last step (valid rows: finished envs)."""
+        torch = _torch()
+        if self.collect_states:
+            return self._terminal_old_states.cpu().numpy()
+        keep = self.obs_aos.clone()
+        self._export_obs(self.terminal)
+        out = torch.view_as_complex(self.obs_aos).cpu().numpy()
+        self.obs_aos.copy_(keep)
+        return out
+
+    def _step_collect_states(self, host):
+        torch = _torch()
+        N = self.num_envs
+        a_w = self.action_dev.shape[1]
+        if self._kernel_n_act > 0:
+            self.action_dev.copy_(host["action"], non_blocking=True)
+        self._launch_step(self.action_dev.data_ptr() if self._kernel_n_act else None, a_w,
+                          2 if self.free_action_space else 1)
+        if self.autoreset:
+            self._reset_done_envs()
+        self._invalidate()
+        obs = torch.view_as_complex(self.old_states).cpu().numpy()
+        flags = self.flags[:N].cpu().numpy()
+        dones = (flags & _lib.FLAG_DONE).astype(bool)
+        lam = self.info_lam[:, :N].cpu().numpy()
+        niter = self.info_niter[:N].cpu().numpy()
+        truncated_key = niter >= MAX_EPISODE_STEPS[self.envname] if self.envname == "sdc-v1" else np.ones(N, bool)
+        infos = LazyInfos(niter, self.info_residual[:N].cpu().numpy(), lam[0] + 1j * lam[1], dones, truncated_key,
+                          self._fetch_terminal)
+        infos.flags = flags
+        return obs, self.reward[:N].cpu().numpy(), dones, infos
+
+    # ------------------------------------------------------------------ state injection (tests, dp_playground)
+    def set_state(self, u, r, niter=None):
+        """Overwrite (u, r) of all envs from host arrays (N, M) complex128 (the reference's ``env.state = ...``)."""
+        torch = _torch()
+        N, M = self.num_envs, self.M
+        obs = np.stack([np.asarray(u, dtype=np.complex128).reshape(N, M), np.asarray(r, dtype=np.complex128).reshape(N, M)], axis=1)
+        t = torch.view_as_real(torch.as_tensor(np.ascontiguousarray(obs))).to(self.device).contiguous()
+        _lib.check(self._L.sdcgym_import_obs(M, N, self.ld, t.data_ptr(), self.S.data_ptr(), self._stream()),
+                   "sdcgym_import_obs")
+        _lib.check(self._L.sdcgym_refresh_resnorm(M, N, self.ld, self.S.data_ptr(), self.resnorm.data_ptr(),
+                                                  self._stream()), "sdcgym_refresh_resnorm")
+        if niter is not None:
+            self.niter[:N] = torch.as_tensor(np.asarray(niter, dtype=np.int32)).to(self.device)
+        torch.cuda.current_stream(self.device).synchronize()  # `t` must outlive the kernels
+        self._invalidate()
+
+    # ------------------------------------------------------------------ VecEnv odds and ends
+    def get_attr(self, name, indices=None):
+        idx = range(self.num_envs) if indices is None else indices
+        return [getattr(self.envs[i], name) for i in idx]
+
+    def set_attr(self, name, value, indices=None):
+        if name == "num_episodes":
+            self.set_num_episodes(value, indices)
+        else:
+            raise AttributeError(f"cannot set {name!r} on a batched env")
+
+    def env_method(self, name, *args, indices=None, **kwargs):
+        if name == "set_num_episodes":
+            self.set_num_episodes(*args, indices=indices, **kwargs)
+            return [None] * (self.num_envs if indices is None else len(indices))
+        raise AttributeError(name)
+
+    def state_dict(self):
+        """Checkpointable env state (device tensors cloned to host)."""
+        N = self.num_envs
+        return {k: getattr(self, k)[..., :N].cpu() for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr")} | {
+            "seed": int(self._desc.seed)}
+
+    def load_state_dict(self, sd):
+        N = self.num_envs
+        for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
+            getattr(self, k)[..., :N].copy_(sd[k].to(self.device))
+        self._desc.seed = int(sd["seed"])
+        self._invalidate()
+
+    def close(self):
+        self._host = None
+
+    def render(self, *a, **k):  # pragma: no cover
+        raise NotImplementedError

@@ -1,0 +1,148 @@
+// tests/host_shim/shim.cpp - TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the very templates the CUDA kernels instantiate (sdc_gym_b200/csrc/*.cuh: step_one, reset_one,
+// rho_one, cinv_exact, ...) for the host with g++, and runs them over host arrays one "thread" at a time.
+// This lets the CPU-only test suite (`-m "not gpu"`) catch logic errors in the kernel bodies before GPU time
+// is spent.  It is never loaded by the sdc_gym_b200 package and is not a fallback: same C ABI structs,
+// symbols prefixed `shim_`.
+//
+// Build: g++ -O1 -std=c++17 -fPIC -shared -ffp-contract=off -mfma -x c++ shim.cpp  (tests/host_shim/build.py)
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+using std::isnan;
+using std::isinf;
+
+#include "../../sdc_gym_b200/csrc/step_params.cuh"
+#include "../../sdc_gym_b200/csrc/specrad.cuh"
+
+using namespace sdcgym;
+
+extern "C" int sdcgym_num_actions(int M, int prec_type) {
+    switch (prec_type) {
+    case SDCGYM_PREC_DIAG: return M;
+    case SDCGYM_PREC_LOWER_DIAG: return M - 1;
+    case SDCGYM_PREC_LOWER_TRI: return M * (M + 1) / 2;
+    case SDCGYM_PREC_STRICTLY_LOWER_TRI: return M * (M - 1) / 2;
+    default: return 0;
+    }
+}
+
+template <int M>
+static int reset_m(const sdcgym_env_desc* d, const sdcgym_state* st, const double* lam_in, const uint8_t* mask,
+                   double* old_states) {
+    StepParams<M> p;
+    fill_params<M>(p, d, st);
+    p.lam_in = lam_in;
+    p.mask = mask;
+    p.old_states = old_states;
+    for (int64_t i = 0; i < p.N; i++) {
+        if (d->blas_variant == 0) reset_one<M, 0>(p, i);
+        else reset_one<M, 1>(p, i);
+    }
+    return 0;
+}
+
+template <int M>
+static int step_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    StepParams<M> p;
+    fill_params<M>(p, d, st);
+    fill_step_io<M>(p, io);
+    const bool dense = d->prec_type != SDCGYM_PREC_DIAG, full = d->env_kind == SDCGYM_ENV_FULL;
+    constexpr int HD = HoldPolicy<M>::diag, HS = HoldPolicy<M>::dense;
+    // emulate whole thread blocks so the i >= N clamping path is exercised too
+    const int64_t nthreads = (p.N + kBlock - 1) / kBlock * kBlock;
+    for (int64_t i = 0; i < nthreads; i++) {
+        if (d->blas_variant == 0) {
+            if (full) { if (dense) step_one<M, 0, 0, true, HS>(p, i); else step_one<M, 0, 0, false, HD>(p, i); }
+            else      { if (dense) step_one<M, 1, 0, true, HS>(p, i); else step_one<M, 1, 0, false, HD>(p, i); }
+        } else {
+            if (full) { if (dense) step_one<M, 0, 1, true, HS>(p, i); else step_one<M, 0, 1, false, HD>(p, i); }
+            else      { if (dense) step_one<M, 1, 1, true, HS>(p, i); else step_one<M, 1, 1, false, HD>(p, i); }
+        }
+    }
+    return 0;
+}
+
+
+extern "C" int shim_reset(const sdcgym_env_desc* d, const sdcgym_state* st, const double* lam_in, const uint8_t* mask,
+                          double* old_states) {
+    switch (d->M) {
+    case 2: return reset_m<2>(d, st, lam_in, mask, old_states);
+    case 3: return reset_m<3>(d, st, lam_in, mask, old_states);
+    case 4: return reset_m<4>(d, st, lam_in, mask, old_states);
+    case 5: return reset_m<5>(d, st, lam_in, mask, old_states);
+    case 6: return reset_m<6>(d, st, lam_in, mask, old_states);
+    case 7: return reset_m<7>(d, st, lam_in, mask, old_states);
+    case 8: return reset_m<8>(d, st, lam_in, mask, old_states);
+    case 9: return reset_m<9>(d, st, lam_in, mask, old_states);
+    }
+    return -2;
+}
+
+extern "C" int shim_step(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    switch (d->M) {
+    case 2: return step_m<2>(d, st, io);
+    case 3: return step_m<3>(d, st, io);
+    case 4: return step_m<4>(d, st, io);
+    case 5: return step_m<5>(d, st, io);
+    case 6: return step_m<6>(d, st, io);
+    case 7: return step_m<7>(d, st, io);
+    case 8: return step_m<8>(d, st, io);
+    case 9: return step_m<9>(d, st, io);
+    }
+    return -2;
+}
+
+// ---- spectral radius ----
+#include "../../sdc_gym_b200/csrc/specrad_params.cuh"
+
+template <int M>
+static int rho_m(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, double* rho) {
+    RhoParams<M> p;
+    fill_rho_params<M>(p, d, N, lam, qd, rho);
+    for (int64_t i = 0; i < N; i++) rho_one<M>(p, i);
+    return 0;
+}
+
+extern "C" int shim_spectral_radius(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, double* rho) {
+    switch (d->M) {
+    case 2: return rho_m<2>(d, N, lam, qd, rho);
+    case 3: return rho_m<3>(d, N, lam, qd, rho);
+    case 4: return rho_m<4>(d, N, lam, qd, rho);
+    case 5: return rho_m<5>(d, N, lam, qd, rho);
+    case 6: return rho_m<6>(d, N, lam, qd, rho);
+    case 7: return rho_m<7>(d, N, lam, qd, rho);
+    case 8: return rho_m<8>(d, N, lam, qd, rho);
+    case 9: return rho_m<9>(d, N, lam, qd, rho);
+    }
+    return -2;
+}
+
+// ---- direct access to the exact inverse template (row-major complex in/out) ----
+template <int M>
+static void cinv_m(const double* P, double* out, int variant) {
+    cplx A[M * M], B[M * M];
+    for (int r = 0; r < M; r++)
+        for (int c = 0; c < M; c++) A[r + c * M] = cplx{P[(r * M + c) * 2], P[(r * M + c) * 2 + 1]};
+    if (variant == 0) cinv_exact<M, 0>(A, B);
+    else cinv_exact<M, 1>(A, B);
+    for (int r = 0; r < M; r++)
+        for (int c = 0; c < M; c++) {
+            out[(r * M + c) * 2] = B[r + c * M].re;
+            out[(r * M + c) * 2 + 1] = B[r + c * M].im;
+        }
+}
+extern "C" int shim_cinv(int M, const double* P, double* out, int variant) {
+    switch (M) {
+    case 2: cinv_m<2>(P, out, variant); return 0;
+    case 3: cinv_m<3>(P, out, variant); return 0;
+    case 4: cinv_m<4>(P, out, variant); return 0;
+    case 5: cinv_m<5>(P, out, variant); return 0;
+    case 6: cinv_m<6>(P, out, variant); return 0;
+    case 7: cinv_m<7>(P, out, variant); return 0;
+    case 8: cinv_m<8>(P, out, variant); return 0;
+    case 9: cinv_m<9>(P, out, variant); return 0;
+    }
+    return -2;
+}
