@@ -24,6 +24,8 @@ NVCC_FLAGS = [
     "-fmad=false",  # never contract a*b+c: every FMA in the kernels is an explicit __fma_rn
     "-Xcompiler", "-fPIC",
 ]
+if os.environ.get("SDCGYM_TUNE_VARIANTS") == "1":  # experiment builds only: extra (occupancy, residency) variants
+    NVCC_FLAGS.append("-DSDCGYM_TUNE_VARIANTS")
 
 
 def _nvcc() -> str:

@@ -1,6 +1,8 @@
 // step_inst.cu - one translation unit per collocation size: compiled once for every M in 2..9 with
 // -DSDCGYM_M=<M> (sdc_gym_b200/build.py) so the eight heavy instantiation sets build in parallel.
 // Exposes sdcgym_launch_reset_m<M> / sdcgym_launch_step_m<M>, dispatched from sdcgym_abi.cu.
+#include <cstdlib>
+
 #include "step_params.cuh"
 
 #ifndef SDCGYM_M
@@ -16,10 +18,48 @@ constexpr int kM = SDCGYM_M;
 constexpr int kHoldDiag = HoldPolicy<kM>::diag;
 constexpr int kHoldDense = HoldPolicy<kM>::dense;
 
+#ifdef SDCGYM_TUNE_VARIANTS
+// Tuning knob for experiments (not part of the ABI): SDCGYM_TUNE=<n> selects a (min blocks/SM, C residency)
+// variant of the M=5 diagonal full-solve kernel.  0 / unset = the shipped default.
+static int tune_variant() {
+    const char* e = getenv("SDCGYM_TUNE");
+    return e ? atoi(e) : 0;
+}
+#endif
+
 template <int KIND, int V, bool DENSE>
 static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + kBlock - 1) / kBlock);
-    step_kernel<kM, KIND, V, DENSE, (DENSE ? kHoldDense : kHoldDiag)><<<grid, kBlock, 0, s>>>(p);
+#ifdef SDCGYM_TUNE_VARIANTS
+    if constexpr (kM == 5 && KIND == SDCGYM_ENV_FULL && !DENSE && V == 0) {
+        switch (tune_variant()) {
+        case 1: step_kernel<kM, KIND, V, DENSE, 2, 2><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 2: step_kernel<kM, KIND, V, DENSE, 2, 3><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 3: step_kernel<kM, KIND, V, DENSE, 2, 4><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 4: step_kernel<kM, KIND, V, DENSE, 1, 3><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 5: step_kernel<kM, KIND, V, DENSE, 0, 3><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 6: step_kernel<kM, KIND, V, DENSE, 0, 4><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 7: step_kernel<kM, KIND, V, DENSE, 0, 5><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 8: step_kernel<kM, KIND, V, DENSE, 0, 6><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+        case 9: step_kernel<kM, KIND, V, DENSE, 1, 4><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
+#define SDCGYM_TV(n, HOLD, MINB, BLK)                                                                      \
+        case n: step_kernel<kM, KIND, V, DENSE, HOLD, MINB, BLK><<<(unsigned)((p.N + BLK - 1) / BLK), BLK, 0, s>>>(p); \
+            return cudaGetLastError();
+        SDCGYM_TV(10, 1, 6, 64)
+        SDCGYM_TV(11, 0, 8, 64)
+        SDCGYM_TV(12, 2, 4, 64)
+        SDCGYM_TV(13, 1, 12, 32)
+        SDCGYM_TV(14, 1, 5, 64)
+        SDCGYM_TV(15, 1, 2, 256)
+        SDCGYM_TV(16, 0, 2, 256)
+        SDCGYM_TV(17, 1, 4, 96)
+#undef SDCGYM_TV
+        default: break;
+        }
+    }
+#endif
+    step_kernel<kM, KIND, V, DENSE, (DENSE ? kHoldDense : kHoldDiag),
+                (DENSE ? HoldPolicy<kM>::dense_minb : HoldPolicy<kM>::diag_minb)><<<grid, kBlock, 0, s>>>(p);
     return cudaGetLastError();
 }
 

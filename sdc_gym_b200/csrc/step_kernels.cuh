@@ -153,7 +153,7 @@ SDCGYM_HD void reset_one(const StepParams<M>& p, int64_t i) {
     double ur[M], ui[M], rr[M], ri[M];
     initial_state<M, V>(p.Q, zr, zi, ur, ui, rr, ri);
     store_state<M>(p.S, p.ld, i, ur, ui, rr, ri);
-    p.resnorm[i] = inf_norm<M>(rr, ri);
+    p.resnorm[i] = inf_norm_fast<M>(rr, ri);
     if (p.old_states) {
         store_column<M>(p.old_states, i, p.max_iters, 0, ur, ui, rr, ri);
         double* base = p.old_states + (size_t)i * (2 * M) * p.max_iters * 2;
@@ -355,6 +355,13 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
 
     // one sweep: u += Pinv @ r ; r = u0 - C @ u      (sdc_env.py:229-231 / :516-519)
     auto sweep = [&]() {
+        // when C is not register resident its entries are re-derived from z and the constant-bank Q on every
+        // sweep; the empty asm keeps the compiler from hoisting those products back out of the loop (which
+        // would turn them into spills).
+        double zr_s = zr, zi_s = zi;
+#ifdef __CUDA_ARCH__
+        if (HOLD < 2) asm volatile("" : "+d"(zr_s), "+d"(zi_s));
+#endif
         double dr[M], di[M];
 #pragma unroll
         for (int m = 0; m < M; m++) {
@@ -382,9 +389,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
             for (int c = 0; c < M; c++) {
                 double q = p.Q[m * M + c];
                 if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1) ? m * M + c : 0];
-                else cr[c] = (m == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
+                else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
                 if (HOLD >= 2) ci[c] = Ci[(HOLD >= 2) ? m * M + c : 0];
-                else ci[c] = -dmul(zi, q);
+                else ci[c] = -dmul(zi_s, q);
             }
             zgemv_rowdot<M, V>(cr, ci, ur, ui, yr, yi);
             rr[m] = dsub(1.0, yr);
@@ -399,33 +406,50 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
     if (KIND == SDCGYM_ENV_FULL) {
         // while not done and niter < max_iters  (sdc_env.py:224-247); per-lane early exit by warp vote
         const HiBand bc = make_band(p.restol), be = make_band(thr);
+        const SqBand sc = make_sqband(p.restol), se = make_sqband(thr);
         bool act = p.max_iters > 0;
-        bool have_nr = false;
         while (SDCGYM_WARP_ANY(act)) {
             if (act) {
                 it++;
                 sweep();
+                // decide `err` (nr is NaN/Inf or nr > thr) and `conv` (nr < restol) without forming nr:
+                // stage 1 on the integer pipe, stage 2 on squared magnitudes, exact norm as a last resort.
                 const int H = absmax_hi<M>(rr, ri);
-                have_nr = false;
+                const bool amb_e = (H > be.lo) && (H < be.hi), amb_c = (H > bc.lo) && (H < bc.hi);
                 if (H >= be.hi) {
                     err = true;  // NaN / Inf / > 100 x
-                } else if (H > be.lo || (H > bc.lo && H < bc.hi)) {
-                    // inside an ambiguity band: decide on the exact norm, as the reference does
-                    nr = inf_norm<M>(rr, ri);
-                    have_nr = true;
-                    err = isnan(nr) || isinf(nr) || nr > thr;
-                    if (!err) conv = nr < p.restol;
-                } else {
+                } else if (!(amb_e || amb_c)) {
                     conv = H <= bc.lo;
+                } else {
+                    const double s2 = sq_absmax<M>(rr, ri);
+                    // 0 = surely below the threshold, 1 = surely above, 2 = undecided
+                    const int ge = !amb_e ? 0 : (!se.ok ? 2 : (s2 < se.lo2 ? 0 : (s2 > se.hi2 ? 1 : 2)));
+                    const int gc = !amb_c ? (H <= bc.lo ? 0 : 1) : (!sc.ok ? 2 : (s2 < sc.lo2 ? 0 : (s2 > sc.hi2 ? 1 : 2)));
+                    if (ge == 2 || gc == 2) {
+                        // copy first: passing rr/ri themselves would force a store of both arrays to local
+                        // memory on every sweep, not just here
+                        double tr[M], ti[M];
+#pragma unroll
+                        for (int m = 0; m < M; m++) {
+                            tr[m] = rr[m];
+                            ti[m] = ri[m];
+                        }
+                        const double nx = inf_norm_slow<M>(tr, ti);
+                        err = isnan(nx) || isinf(nx) || nx > thr;
+                        if (!err) conv = nx < p.restol;
+                    } else {
+                        err = ge == 1;
+                        conv = !err && gc == 0;
+                    }
                 }
                 if (p.old_states && valid && it < p.max_iters) store_column<M>(p.old_states, i, p.max_iters, it, ur, ui, rr, ri);
                 act = !err && !conv && it < p.max_iters;
             }
         }
-        if (!have_nr && p.max_iters > 0) nr = inf_norm<M>(rr, ri);
+        if (p.max_iters > 0) nr = inf_norm_fast<M>(rr, ri);
     } else {
         sweep();
-        nr = inf_norm<M>(rr, ri);
+        nr = inf_norm_fast<M>(rr, ri);
         it++;
         err = isnan(nr) || isinf(nr);
         err = err || nr > thr;
@@ -481,7 +505,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
         const double nzr = dmul(nlr, p.dt), nzi = dmul(nli, p.dt);
         initial_state<M, V>(p.Q, nzr, nzi, ur, ui, rr, ri);
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);
-        p.resnorm[i] = inf_norm<M>(rr, ri);
+        p.resnorm[i] = inf_norm_fast<M>(rr, ri);
         p.niter[i] = 0;
     } else {
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);
@@ -496,9 +520,9 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
     reset_one<M, V>(p, (int64_t)blockIdx.x * kBlock + threadIdx.x);
 }
 
-template <int M, int KIND, int V, bool DENSE, int HOLD>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepParams<M> p) {
-    step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * kBlock + threadIdx.x);
+template <int M, int KIND, int V, bool DENSE, int HOLD, int MINB = 1, int BLOCK = kBlock>
+__global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepParams<M> p) {
+    step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x);
 }
 #endif
 

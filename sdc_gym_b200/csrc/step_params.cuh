@@ -66,12 +66,16 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
     p.old_states = io->old_states;
 }
 
-// register-residency policy for C (see step_kernels.cuh): diag kernels hold Re+Im up to M=5, Re only up to
-// M=7; dense kernels spend their registers on the M x M inverse instead.
+// Register-residency policy for C and occupancy target (measured on B200, profiles/tuning_r01.md):
+// diag kernels keep Re(C) in registers and re-derive Im(C) = -zi*q from the constant bank (166 registers,
+// 3 blocks of 128 threads per SM) up to M=5, Re only up to M=7, nothing beyond; dense kernels spend their
+// registers on the M x M inverse instead.
 template <int M>
 struct HoldPolicy {
-    static constexpr int diag = (M <= 5) ? 2 : ((M <= 7) ? 1 : 0);
+    static constexpr int diag = (M <= 7) ? 1 : 0;
+    static constexpr int diag_minb = (M <= 5) ? 3 : 2;
     static constexpr int dense = (M <= 3) ? 2 : 0;
+    static constexpr int dense_minb = 2;
 };
 
 }  // namespace sdcgym

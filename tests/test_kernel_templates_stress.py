@@ -1,0 +1,76 @@
+"""CPU: kernel templates (host shim) against the C oracle on seeded batches large enough to exercise the
+integer band / squared-magnitude / exact-norm decision stages and the single-candidate fast norm."""
+import numpy as np
+import pytest
+
+from oracle import exact
+from sdc_gym_b200.collocation import collocation_matrix
+from sdc_gym_b200.precond import fixed_preconditioner, num_actions
+from tests import host_shim
+from tests.helpers import assert_reward_close, assert_same
+
+
+def _run(kind, M, n, *, prec=None, prec_type="diag", mode="good", steps=1, strategy="iteration_only", seed=0,
+         im_int=(-10, 0), variant=0):
+    rng = np.random.default_rng(seed)
+    Q = collocation_matrix(M)
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(im_int[0], im_int[1], n)
+    d = host_shim.make_desc(kind, M, prec=prec, prec_type=prec_type, do_scale=(prec_type == "diag"), strategy=strategy,
+                            variant=variant)
+    b = host_shim.ShimBatch(d, n)
+    u, r = b.reset(lam)
+    ou, orr = exact.reset(Q, 1.0, lam, variant)
+    assert_same(u, ou); assert_same(r, orr)
+    assert_same(b.resnorm[:n], np.abs(orr).max(axis=1), "resnorm after reset")
+    rinit, niter = orr.copy(), np.zeros(n, np.int32)
+    A = 0 if prec else num_actions(M, prec_type)
+    Qd = fixed_preconditioner(prec, M, Q) if prec else None
+    alive = np.ones(n, bool)
+    for s in range(steps):
+        if prec:
+            act = None
+        elif prec_type == "diag" and mode == "good" and M in (3, 5, 7):
+            act = 2 * (np.diag(fixed_preconditioner("min", M))[None] + rng.uniform(-0.03, 0.03, (n, M))) - 1
+        elif prec_type == "diag":
+            act = rng.uniform(-1, 1, (n, A))
+        else:
+            act = rng.uniform(0, 0.5, (n, A))
+        out = b.step(act)
+        o = exact.step(kind, Q, 1.0, lam, ou, orr, niter, rinit, act, prec_type="fixed" if prec else prec_type,
+                       Qd_fixed=Qd, do_scale=(prec_type == "diag"), reward_strategy=strategy, variant=variant)
+        assert_same(out["u"][alive], ou[alive], f"step {s} u"); assert_same(out["r"][alive], orr[alive], f"step {s} r")
+        assert np.array_equal(out["niter"][alive], niter[alive]), f"step {s} niter"
+        assert_same(out["residual"][alive], o["resnorm"][alive], f"step {s} residual")
+        assert np.array_equal(out["err"][alive], o["err"][alive])
+        assert_reward_close(out["reward"][alive], o["reward"][alive])
+        if kind == "sdc-v1":
+            assert np.array_equal(out["done"][alive], o["done"][alive])
+            alive &= ~o["done"]
+        else:
+            assert np.array_equal(out["conv"][alive], o["done"][alive])
+    return niter
+
+
+@pytest.mark.parametrize("M", [3, 5, 7, 9])
+def test_v0_diag_good_and_uniform(M):
+    nit = _run("sdc-v0", M, 3000, mode="good", seed=M)
+    if M != 9:
+        assert (nit < 50).any()
+    _run("sdc-v0", M, 1500, mode="uniform", seed=50 + M)
+
+
+def test_v0_real_lambda_ties_and_variant1():
+    _run("sdc-v0", 5, 1500, mode="good", seed=3, im_int=(0, 0))
+    _run("sdc-v0", 5, 1500, mode="good", seed=4, variant=1)
+    _run("sdc-v0", 3, 1500, mode="good", seed=5, variant=1)
+
+
+@pytest.mark.parametrize("prec", ["LU", "min", "EE"])
+def test_v0_fixed(prec):
+    _run("sdc-v0", 5, 1000, prec=prec, seed=7)
+
+
+def test_v0_lower_tri_and_v1_rollout():
+    _run("sdc-v0", 5, 600, prec_type="lower_tri", seed=8)
+    _run("sdc-v1", 5, 300, mode="good", steps=50, strategy="residual_change", seed=9)
+    _run("sdc-v1", 7, 200, prec="LU", steps=30, strategy="residual_change", seed=10)
