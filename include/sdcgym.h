@@ -167,6 +167,39 @@ typedef struct sdcgym_rho_desc {
 int sdcgym_spectral_radius(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, double* rho,
                            void* stream);
 
+/*
+ * ResidualLoss.take_step (dp_playground.py:247-258) for N samples: u' = u + inv(I - lam*dt*Qd) r_old,
+ * r' = u0 - C u', norm = ||r'||_inf.  lam [N], u0/u/r_old/u_out/r_out [N][M] complex128 interleaved,
+ * qd as in sdcgym_spectral_radius, Cs [N][M][M] complex128 or NULL (then C = I - lam*dt*Q is formed on the fly).
+ * JAX arithmetic in the reference: agreement is to rounding level (1e-12 relative), not bit-exact.
+ */
+int sdcgym_residual_step(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, const double* Cs,
+                         const double* u0, const double* u, const double* r_old, double* u_out, double* r_out,
+                         double* norm_out, void* stream);
+
+/*
+ * Device-side VecNormalize building blocks (SB3 RunningMeanStd semantics; utils/utils.py:295-312).
+ * Planes X[P][ld] (observation planes S, or a single reward/return plane with P = 1).
+ *   accumulate : sums[p] = sum_i (x_pi - shift_p), sums[P+p] = sum_i (x_pi - shift_p)^2   (deterministic tree;
+ *                scratch needs sdcgym_vecnorm_scratch_doubles(P) doubles).  `sums` of several ranks may be
+ *                all-reduced before the merge; shift must then be identical on all ranks (use the running mean).
+ *   merge      : Chan update of (mean[P], var[P], count) with a batch of `batch_count` samples described by
+ *                `sums` taken with shift == mean.  count2 = {count, scratch}.
+ *   apply      : Y = clip((X - mean) / sqrt(var + eps), -clip, clip)
+ *   returns    : ret = ret * gamma + reward
+ *   reward     : out = normalize ? clip(reward / sqrt(ret_var + eps), +-clip) : reward; ret = 0 where DONE
+ */
+int sdcgym_vecnorm_scratch_doubles(int P);
+int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift, double* scratch,
+                              double* sums, void* stream);
+int sdcgym_vecnorm_merge(int P, double batch_count, const double* sums, double* mean, double* var, double* count2,
+                         void* stream);
+int sdcgym_vecnorm_apply(int P, int64_t N, int64_t ld, const double* X, const double* mean, const double* var, double eps,
+                         double clip, double* Y, void* stream);
+int sdcgym_vecnorm_returns(int64_t N, const double* reward, double gamma, double* returns, void* stream);
+int sdcgym_vecnorm_reward(int64_t N, const double* reward, const uint8_t* flags, const double* ret_var, double eps,
+                          double clip, int normalize, double* out, double* returns, void* stream);
+
 /* sum of x[0..N) in fp64 with a fixed (N-independent per block, deterministic) reduction tree -> out[0] */
 int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream);
 

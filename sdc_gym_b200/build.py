@@ -68,11 +68,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for M in M_VALUES:
         jobs.append(([nvcc, *NVCC_FLAGS, f"-DSDCGYM_M={M}", "-c", os.path.join(CSRC, "step_inst.cu"),
                       "-o", os.path.join(OBJ_DIR, f"step_m{M}.o")]))
-    for name in ("sdcgym_abi", "specrad", "hostpipe"):
+    for name in ("sdcgym_abi", "specrad", "vecnorm", "hostpipe"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             # the spectral-radius kernel follows no prescribed rounding sequence: let it contract FMAs
-            flags = [f for f in NVCC_FLAGS if not (name == "specrad" and f == "-fmad=false")]
+            flags = [f for f in NVCC_FLAGS if not (name in ("specrad", "vecnorm") and f == "-fmad=false")]
             jobs.append([nvcc, *flags, "-c", src, "-o", os.path.join(OBJ_DIR, name + ".o")])
     workers = max(1, min(len(jobs), os.cpu_count() or 1))
     with concurrent.futures.ThreadPoolExecutor(workers) as ex:

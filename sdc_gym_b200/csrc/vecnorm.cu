@@ -1,0 +1,280 @@
+// vecnorm.cu - device-side VecNormalize (SB3 semantics restated: RunningMeanStd with Chan's merge, clip to
+// +-clip) over the observation planes and the reward/return planes, plus the ResidualLoss sweep.
+//
+// Reference call sites: utils/utils.py:295-312 (VecNormalize(env, norm_obs, norm_reward, gamma)),
+// dp_playground.py:235-258 (ResidualLoss.take_step).  SB3 itself is third-party and not installed: its
+// documented semantics are restated ("parity unpinned").  Complex observations are normalised on
+// their re / im planes separately (SB3 on complex128 is ill-defined).
+//
+// All reductions use a fixed block count and a fixed summation tree: deterministic run to run.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/sdcgym.h"
+#include "specrad.cuh"
+
+namespace sdcgym {
+
+constexpr int kAccBlocks = 64, kAccThreads = 256;
+
+__device__ __forceinline__ double2 block_sum2(double a, double b) {
+    __shared__ double sa[kAccThreads / 32], sb[kAccThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sa[threadIdx.x >> 5] = a;
+        sb[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    a = (threadIdx.x < kAccThreads / 32) ? sa[threadIdx.x] : 0.0;
+    b = (threadIdx.x < kAccThreads / 32) ? sb[threadIdx.x] : 0.0;
+    if (threadIdx.x < 32)
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+    __syncthreads();
+    return make_double2(a, b);
+}
+
+// partial[(p*kAccBlocks + b)*2 + {0,1}] = sum over this block's strided slice of (x - shift_p), (x - shift_p)^2
+__global__ void __launch_bounds__(kAccThreads) acc_partial_kernel(int64_t N, int64_t ld, const double* __restrict__ X,
+                                                                  const double* __restrict__ shift,
+                                                                  double* __restrict__ partial) {
+    const int p = blockIdx.y;
+    const double s = shift ? shift[p] : 0.0;
+    const double* x = X + (int64_t)p * ld;
+    double a = 0.0, b = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < N; i += (int64_t)kAccBlocks * kAccThreads) {
+        const double d = x[i] - s;
+        a += d;
+        b += d * d;
+    }
+    double2 r = block_sum2(a, b);
+    if (threadIdx.x == 0) {
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
+    }
+}
+__global__ void acc_final_kernel(int P, const double* __restrict__ partial, double* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < kAccBlocks; k++) {
+        a += partial[((int64_t)p * kAccBlocks + k) * 2];
+        b += partial[((int64_t)p * kAccBlocks + k) * 2 + 1];
+    }
+    out[p] = a;
+    out[P + p] = b;
+}
+
+// RunningMeanStd.update_from_moments with the batch given as shifted sums (shift = the running mean itself)
+__global__ void rms_merge_kernel(int P, double batch_count, const double* __restrict__ sums, double* __restrict__ mean,
+                                 double* __restrict__ var, double* __restrict__ count) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const double n = count[0];
+    if (p < P && batch_count > 0) {
+        const double d1 = sums[p] / batch_count;                 // batch_mean - running mean
+        const double bvar = fmax(sums[P + p] / batch_count - d1 * d1, 0.0);  // population variance of the batch
+        const double tot = n + batch_count;
+        const double m2 = var[p] * n + bvar * batch_count + d1 * d1 * n * batch_count / tot;
+        mean[p] = mean[p] + d1 * batch_count / tot;
+        var[p] = m2 / tot;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && batch_count > 0) count[1] = n + batch_count;  // committed by the host-side swap
+}
+__global__ void rms_commit_kernel(double* __restrict__ count) { count[0] = count[1]; }
+
+__global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X, const double* __restrict__ mean,
+                             const double* __restrict__ var, double eps, double clip, double* __restrict__ Y) {
+    const int p = blockIdx.y;
+    const double m = mean[p], is = 1.0 / sqrt(var[p] + eps);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = (X[(int64_t)p * ld + i] - m) * is;
+        Y[(int64_t)p * ld + i] = fmin(fmax(v, -clip), clip);
+    }
+}
+
+__global__ void returns_kernel(int64_t N, const double* __restrict__ reward, double gamma, double* __restrict__ ret) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) ret[i] = ret[i] * gamma + reward[i];
+}
+__global__ void reward_apply_kernel(int64_t N, const double* __restrict__ reward, const uint8_t* __restrict__ flags,
+                                    const double* __restrict__ ret_var, double eps, double clip, int normalize,
+                                    double* __restrict__ out, double* __restrict__ ret) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double r = reward[i];
+    if (normalize) r = fmin(fmax(r / sqrt(ret_var[0] + eps), -clip), clip);
+    out[i] = r;
+    if (ret && flags && (flags[i] & SDCGYM_FLAG_DONE)) ret[i] = 0.0;
+}
+
+// ---- ResidualLoss.take_step (dp_playground.py:247-258): u' = u + P^{-1} r_old, r' = u0 - C u', ||r'||inf -------
+template <int M>
+struct ResParams {
+    double Q[M * M];
+    double Qd[M * M];
+    int64_t N;
+    const double *lam, *qd, *Cs, *u0, *u, *r_old;
+    double *u_out, *r_out, *norm_out;
+    double dt;
+    int32_t prec_type, qd_is_complex, n_act;
+};
+
+template <int M>
+__global__ void __launch_bounds__(128) residual_step_kernel(const __grid_constant__ ResParams<M> p) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= p.N) return;
+    const C2 z{p.lam[2 * i] * p.dt, p.lam[2 * i + 1] * p.dt};
+    C2 Qd[M * M];
+    const int w = p.qd_is_complex ? 2 : 1;
+    const double* row = p.qd ? p.qd + i * (int64_t)p.n_act * w : nullptr;
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < M; r++)
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            C2 d{0.0, 0.0};
+            bool take = false;
+            switch (p.prec_type) {
+            case SDCGYM_PREC_DIAG: take = (c == r); break;
+            case SDCGYM_PREC_LOWER_DIAG: take = (r == c + 1); break;
+            case SDCGYM_PREC_LOWER_TRI: take = (c <= r); break;
+            case SDCGYM_PREC_STRICTLY_LOWER_TRI: take = (c < r); break;
+            default: break;
+            }
+            if (p.prec_type == SDCGYM_PREC_FIXED) d.r = (c <= r) ? p.Qd[r * M + c] : 0.0;
+            else if (take) {
+                d.r = row[k * w];
+                if (p.qd_is_complex) d.i = row[k * w + 1];
+                k++;
+            }
+            Qd[r * M + c] = d;
+        }
+    // delta = P^{-1} r_old by forward substitution, P = I - z Qd (lower triangular)
+    C2 un[M], dl[M];
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+        C2 acc{p.r_old[(i * M + r) * 2], p.r_old[(i * M + r) * 2 + 1]};
+#pragma unroll
+        for (int c = 0; c < r; c++) acc = c_add(acc, c_mul(c_mul(z, Qd[r * M + c]), dl[c]));
+        dl[r] = c_div(acc, c_sub(C2{1.0, 0.0}, c_mul(z, Qd[r * M + r])));
+        un[r] = c_add(C2{p.u[(i * M + r) * 2], p.u[(i * M + r) * 2 + 1]}, dl[r]);
+    }
+    double nrm = 0.0;
+    bool nan = false;
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+        C2 acc{0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            C2 cij;
+            if (p.Cs) cij = C2{p.Cs[((i * M + r) * M + c) * 2], p.Cs[((i * M + r) * M + c) * 2 + 1]};
+            else cij = C2{(r == c ? 1.0 : 0.0) - z.r * p.Q[r * M + c], -z.i * p.Q[r * M + c]};
+            acc = c_add(acc, c_mul(cij, un[c]));
+        }
+        C2 res = c_sub(C2{p.u0[(i * M + r) * 2], p.u0[(i * M + r) * 2 + 1]}, acc);
+        p.u_out[(i * M + r) * 2] = un[r].r;
+        p.u_out[(i * M + r) * 2 + 1] = un[r].i;
+        p.r_out[(i * M + r) * 2] = res.r;
+        p.r_out[(i * M + r) * 2 + 1] = res.i;
+        double a = hypot(res.r, res.i);
+        nan |= isnan(a);
+        nrm = a > nrm ? a : nrm;
+    }
+    p.norm_out[i] = nan ? CUDART_NAN : nrm;
+}
+
+template <int M>
+static int launch_residual(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, const double* Cs,
+                           const double* u0, const double* u, const double* r_old, double* u_out, double* r_out,
+                           double* norm_out, cudaStream_t s) {
+    ResParams<M> p;
+    for (int k = 0; k < M * M; k++) {
+        p.Q[k] = d->Q[k];
+        p.Qd[k] = d->Qd_fixed[k];
+    }
+    p.N = N; p.lam = lam; p.qd = qd; p.Cs = Cs; p.u0 = u0; p.u = u; p.r_old = r_old;
+    p.u_out = u_out; p.r_out = r_out; p.norm_out = norm_out;
+    p.dt = d->dt; p.prec_type = d->prec_type; p.qd_is_complex = d->qd_is_complex;
+    p.n_act = sdcgym_num_actions(M, d->prec_type);
+    residual_step_kernel<M><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace sdcgym
+
+using namespace sdcgym;
+
+extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2; }
+
+extern "C" int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift,
+                                         double* scratch, double* sums, void* stream) {
+    if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if (!X || !scratch || !sums) return SDCGYM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    acc_partial_kernel<<<dim3(kAccBlocks, P), kAccThreads, 0, s>>>(N, ld, X, shift, scratch);
+    acc_final_kernel<<<(P + 63) / 64, 64, 0, s>>>(P, scratch, sums);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_merge(int P, double batch_count, const double* sums, double* mean, double* var,
+                                    double* count2, void* stream) {
+    if (P < 1 || P > 1024) return SDCGYM_EINVAL;
+    if (!sums || !mean || !var || !count2) return SDCGYM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    rms_merge_kernel<<<1, 1024, 0, s>>>(P, batch_count, sums, mean, var, count2);
+    if (batch_count > 0) rms_commit_kernel<<<1, 1, 0, s>>>(count2);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_apply(int P, int64_t N, int64_t ld, const double* X, const double* mean, const double* var,
+                                    double eps, double clip, double* Y, void* stream) {
+    if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!X || !Y || !mean || !var) return SDCGYM_ENULL;
+    unsigned gx = (unsigned)((N + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    apply_kernel<<<dim3(gx, P), 256, 0, (cudaStream_t)stream>>>(N, ld, X, mean, var, eps, clip, Y);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_returns(int64_t N, const double* reward, double gamma, double* returns, void* stream) {
+    if (N < 0) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!reward || !returns) return SDCGYM_ENULL;
+    returns_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, reward, gamma, returns);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_reward(int64_t N, const double* reward, const uint8_t* flags, const double* ret_var,
+                                     double eps, double clip, int normalize, double* out, double* returns, void* stream) {
+    if (N < 0) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!reward || !out || (normalize && !ret_var)) return SDCGYM_ENULL;
+    reward_apply_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, reward, flags, ret_var, eps, clip,
+                                                                                      normalize, out, returns);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_residual_step(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd,
+                                    const double* Cs, const double* u0, const double* u, const double* r_old,
+                                    double* u_out, double* r_out, double* norm_out, void* stream) {
+    if (!d) return SDCGYM_ENULL;
+    if (!sdcgym_supported(d->M, d->prec_type)) return SDCGYM_EUNSUPPORTED;
+    if (N < 0) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!lam || !u0 || !u || !r_old || !u_out || !r_out || !norm_out) return SDCGYM_ENULL;
+    if (d->prec_type != SDCGYM_PREC_FIXED && !qd) return SDCGYM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (d->M) {
+#define C(m) case m: return launch_residual<m>(d, N, lam, qd, Cs, u0, u, r_old, u_out, r_out, norm_out, s);
+        C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)
+#undef C
+    }
+    return SDCGYM_EUNSUPPORTED;
+}

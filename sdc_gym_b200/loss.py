@@ -120,3 +120,48 @@ class SpectralRadiusLoss:
 
 
 NormLoss = SpectralRadiusLoss  # the reference keeps this alias (dp_playground.py:233)
+
+
+class ResidualLoss:
+    """``dp_playground.py:235-258``: one sweep with the learned Q_delta; loss = mean ||r'||_inf.
+
+    ``__call__(lams, outputs, Cs, u0s, us, old_residuals) -> (mean_norm, us', residuals')`` like the reference.
+    ``Cs`` may be ``None`` (the system matrices are then formed from ``lams`` on the device instead of being read).
+    """
+
+    def __init__(self, M, dt, prec_type="diag", *, prec=None, Q=None, device=None):
+        self._sr = SpectralRadiusLoss(M, dt, prec_type, prec=prec, Q=Q, device=device)
+        self.M, self.dt, self.prec_type = self._sr.M, self._sr.dt, self._sr.prec_type
+        self.Q, self.device = self._sr.Q, self._sr.device
+
+    def _c128(self, x, shape):
+        torch = _torch()
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.complex128))
+        t = t.to(self.device).to(torch.complex128).reshape(shape).contiguous()
+        return torch.view_as_real(t)
+
+    def take_step(self, lams, outputs, Cs, u0s, us, old_residuals):
+        torch = _torch()
+        sr, M = self._sr, self.M
+        lam = self._c128(lams, (-1,))
+        B = lam.shape[0]
+        qd, is_c, bc = sr._outputs_tensor(outputs, B)
+        if bc:
+            qd = qd.expand(B, *qd.shape[1:]).contiguous()
+        d = sr._desc
+        d.qd_is_complex, d.qd_broadcast = is_c, 0
+        u0, u, r = (self._c128(x, (B, M)) for x in (u0s, us, old_residuals))
+        C = None if Cs is None else self._c128(Cs, (B, M, M))
+        u_out = torch.empty((B, M, 2), dtype=torch.float64, device=self.device)
+        r_out = torch.empty((B, M, 2), dtype=torch.float64, device=self.device)
+        norms = torch.empty(B, dtype=torch.float64, device=self.device)
+        _lib.check(sr._L.sdcgym_residual_step(
+            ctypes.byref(d), B, lam.data_ptr(), None if qd is None else qd.data_ptr(),
+            None if C is None else C.data_ptr(), u0.data_ptr(), u.data_ptr(), r.data_ptr(), u_out.data_ptr(),
+            r_out.data_ptr(), norms.data_ptr(), sr._stream()), "sdcgym_residual_step")
+        self._keep = (lam, qd, C, u0, u, r)
+        return torch.view_as_complex(u_out), torch.view_as_complex(r_out), norms
+
+    def __call__(self, lams, outputs, Cs, u0s, us, old_residuals):
+        us_new, residuals, norms = self.take_step(lams, outputs, Cs, u0s, us, old_residuals)
+        return self._sr.mean(norms), us_new, residuals

@@ -1,0 +1,238 @@
+"""Device-side ``VecNormalize`` for ``SDCVecEnv`` (reference call site ``utils/utils.py:295-312``).
+
+SB3 semantics restated (SB3 is third-party and not installed here - "parity unpinned"):
+``RunningMeanStd`` starts at mean 0, var 1, count 1e-4 and merges each batch with Chan's formula;
+``obs <- clip((obs - mean) / sqrt(var + eps), +-clip_obs)``; returns ``R <- gamma R + r`` per env (reset on done),
+``reward <- clip(r / sqrt(var_R + eps), +-clip_reward)``; ``terminal_observation`` is normalised too.
+Deviation (documented): the reference feeds complex128 observations to SB3, whose variance/clip on
+complex data is ill-defined; here the statistics are kept per real plane (re and im of every u_m, r_m).
+
+The moments never leave the GPU: accumulate -> (all-reduce over ranks) -> merge -> apply are kernels of
+``libsdcgym.so`` (``csrc/vecnorm.cu``); with several ranks the shifted sums are all-reduced so every rank holds
+the same normaliser (the shift is the running mean, identical everywhere).
+"""
+from __future__ import annotations
+
+import ctypes
+import pickle
+
+import numpy as np
+
+from . import _lib
+from . import dist as _dist_mod
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class _RunningMeanStd:
+    def __init__(self, P, device, epsilon=1e-4):
+        torch = _torch()
+        self.P = P
+        self.mean = torch.zeros(P, dtype=torch.float64, device=device)
+        self.var = torch.ones(P, dtype=torch.float64, device=device)
+        self.count2 = torch.tensor([epsilon, epsilon], dtype=torch.float64, device=device)
+
+    @property
+    def count(self):
+        return float(self.count2[0].item())
+
+    def state(self):
+        return dict(mean=self.mean.cpu().numpy(), var=self.var.cpu().numpy(), count=self.count)
+
+    def load(self, st):
+        torch = _torch()
+        self.mean.copy_(torch.as_tensor(st["mean"]))
+        self.var.copy_(torch.as_tensor(st["var"]))
+        self.count2.fill_(float(st["count"]))
+
+
+class VecNormalize:
+    def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0,
+                 gamma=0.99, epsilon=1e-8, sync=True):
+        torch = _torch()
+        if venv.collect_states:
+            raise NotImplementedError("VecNormalize over collect_states buffers is not supported")
+        self.venv = venv
+        self._L = _lib.load()
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        self.sync = sync
+        self.num_envs = venv.num_envs
+        self.observation_space, self.action_space = venv.observation_space, venv.action_space
+        dev, N, M = venv.device, venv.num_envs, venv.M
+        self.P = 4 * M
+        self.obs_rms = _RunningMeanStd(self.P, dev)
+        self.ret_rms = _RunningMeanStd(1, dev)
+        self.returns = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
+        self.norm_planes = torch.zeros_like(venv.S)
+        self.norm_terminal = torch.zeros_like(venv.S)
+        self.norm_reward_buf = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
+        nscr = self._L.sdcgym_vecnorm_scratch_doubles(self.P)
+        self._scratch = torch.zeros(nscr, dtype=torch.float64, device=dev)
+        self._sums = torch.zeros(2 * self.P + 1, dtype=torch.float64, device=dev)
+        self._rsums = torch.zeros(3, dtype=torch.float64, device=dev)
+        self._obs_aos = torch.zeros((max(N, 1), 2, M, 2), dtype=torch.float64, device=dev)
+        self.old_reward = None
+
+    # ---- delegation --------------------------------------------------------------------------------
+    def __getattr__(self, name):
+        return getattr(self.venv, name)
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.venv.device).cuda_stream)
+
+    def _global_count(self, N):
+        """number of envs over all ranks (static: reduced once, so no per-step host sync)"""
+        if getattr(self, "_global_n", None) is None:
+            torch = _torch()
+            t = torch.tensor([float(N)], dtype=torch.float64, device=self.venv.device)
+            _dist_mod.all_reduce_sum(t)
+            self._global_n = float(t.item())
+        return self._global_n
+
+    # ---- statistics --------------------------------------------------------------------------------
+    def _update(self, rms, planes_ptr, P, N, ld, sums):
+        L, s = self._L, self._stream()
+        _lib.check(L.sdcgym_vecnorm_accumulate(P, N, ld, planes_ptr, rms.mean.data_ptr(), self._scratch.data_ptr(),
+                                               sums.data_ptr(), s), "vecnorm_accumulate")
+        total = float(N)
+        if self.sync and _dist_mod.is_distributed():
+            _dist_mod.all_reduce_sum(sums)  # < 1 kB, latency bound; the only collective of a normalised step
+            total = self._global_count(N)
+        _lib.check(L.sdcgym_vecnorm_merge(P, total, sums.data_ptr(), rms.mean.data_ptr(), rms.var.data_ptr(),
+                                          rms.count2.data_ptr(), s), "vecnorm_merge")
+
+    def _normalize_planes(self, src, dst):
+        v = self.venv
+        _lib.check(self._L.sdcgym_vecnorm_apply(self.P, v.num_envs, v.ld, src.data_ptr(), self.obs_rms.mean.data_ptr(),
+                                                self.obs_rms.var.data_ptr(), self.epsilon, self.clip_obs,
+                                                dst.data_ptr(), self._stream()), "vecnorm_apply")
+
+    def _obs_out(self, planes):
+        """planes (4M, ld) -> (N, 2, M) complex in the env's output mode"""
+        torch = _torch()
+        v = self.venv
+        _lib.check(self._L.sdcgym_export_obs(v.M, v.num_envs, v.ld, planes.data_ptr(), self._obs_aos.data_ptr(),
+                                             self._stream()), "export_obs")
+        t = torch.view_as_complex(self._obs_aos)[: v.num_envs]
+        return t if v.output == "torch" else t.cpu().numpy()
+
+    # ---- VecEnv API --------------------------------------------------------------------------------
+    def reset(self, **kw):
+        v = self.venv
+        v.reset(**kw)
+        self.returns.zero_()
+        if self.norm_obs:
+            if self.training:
+                self._update(self.obs_rms, v.S.data_ptr(), self.P, v.num_envs, v.ld, self._sums)
+            self._normalize_planes(v.S, self.norm_planes)
+            return self._obs_out(self.norm_planes)
+        return self._obs_out(v.S)
+
+    def step_tensor(self, actions=None):
+        """Device-resident normalised step.  Returns the env's dict plus ``obs_planes`` (normalised S planes),
+        ``reward`` replaced by the normalised reward and ``raw_reward``."""
+        v, L, s = self.venv, self._L, self._stream()
+        out = dict(v.step_tensor(actions))
+        N = v.num_envs
+        out["raw_reward"] = out["reward"]
+        if self.norm_obs:
+            if self.training:
+                self._update(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
+            self._normalize_planes(v.S, self.norm_planes)
+            self._normalize_planes(v.terminal, self.norm_terminal)
+            out["obs_planes"], out["terminal"] = self.norm_planes[:, :N], self.norm_terminal[:, :N]
+        else:
+            out["obs_planes"] = v.S[:, :N]
+        if self.training:
+            _lib.check(L.sdcgym_vecnorm_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(), s), "returns")
+            self._update(self.ret_rms, self.returns.data_ptr(), 1, N, max(N, 1), self._rsums)
+        _lib.check(L.sdcgym_vecnorm_reward(N, v.reward.data_ptr(), v.flags.data_ptr(), self.ret_rms.var.data_ptr(),
+                                           self.epsilon, self.clip_reward, int(self.norm_reward),
+                                           self.norm_reward_buf.data_ptr(), self.returns.data_ptr(), s), "reward")
+        out["reward"] = self.norm_reward_buf[:N]
+        return out
+
+    def step(self, actions):
+        """(obs, rewards, dones, infos) with normalised obs / rewards (numpy or torch per the env's ``output``)."""
+        torch = _torch()
+        v = self.venv
+        a = actions
+        if v._kernel_n_act > 0 and not (isinstance(a, torch.Tensor) and a.is_cuda):
+            arr = np.asarray(a, dtype=np.complex128 if v.free_action_space else np.float64).reshape(v.num_envs, -1)
+            a = torch.as_tensor(arr).to(v.device)
+        out = self.step_tensor(a if v._kernel_n_act else None)
+        N = v.num_envs
+        obs = self._obs_out(out["obs_planes"] if self.norm_obs else v.S)
+        self.old_reward = out["raw_reward"]
+        if v.output == "torch":
+            return obs, out["reward"], (out["flags"] & 1).bool(), out
+        from .vec_env import MAX_EPISODE_STEPS, LazyInfos
+
+        flags = out["flags"].cpu().numpy()
+        dones = (flags & 1).astype(bool)
+        niter = out["niter"].cpu().numpy()
+        lam = out["lam"].cpu().numpy()
+        trunc = niter >= MAX_EPISODE_STEPS[v.envname] if v.envname == "sdc-v1" else np.ones(N, bool)
+        term_planes = self.norm_terminal if self.norm_obs else v.terminal
+        infos = LazyInfos(niter, out["residual"].cpu().numpy(), lam[0] + 1j * lam[1], dones, trunc,
+                          lambda: self._terminal_host(term_planes))
+        infos.flags = flags
+        return obs, out["reward"].cpu().numpy(), dones, infos
+
+    def _terminal_host(self, planes):
+        t = self._obs_out(planes)
+        return t.cpu().numpy() if hasattr(t, "cpu") else t
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)
+
+    def get_original_reward(self):
+        return None if self.old_reward is None else self.old_reward.cpu().numpy()
+
+    def get_original_obs(self):
+        return self._obs_out(self.venv.S)
+
+    def normalize_obs(self, obs):
+        """Normalise a host observation array (..., 2, M) complex128 with the current statistics."""
+        mean, var = self.obs_rms.mean.cpu().numpy(), self.obs_rms.var.cpu().numpy()
+        x = np.asarray(obs, dtype=np.complex128)
+        flat = x.reshape(-1, x.shape[-2] * x.shape[-1]).view(np.float64)
+        y = np.clip((flat - mean) / np.sqrt(var + self.epsilon), -self.clip_obs, self.clip_obs)
+        return y.view(np.complex128).reshape(x.shape)
+
+    # ---- persistence (SB3: VecNormalize.save / load, utils/utils.py:415-417) --------------------------------
+    def state_dict(self):
+        return dict(obs_rms=self.obs_rms.state(), ret_rms=self.ret_rms.state(), returns=self.returns.cpu().numpy(),
+                    clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
+                    norm_obs=self.norm_obs, norm_reward=self.norm_reward)
+
+    def load_state_dict(self, sd):
+        torch = _torch()
+        self.obs_rms.load(sd["obs_rms"])
+        self.ret_rms.load(sd["ret_rms"])
+        self.returns.copy_(torch.as_tensor(sd["returns"]))
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
+            setattr(self, k, sd[k])
+
+    def save(self, path):
+        with open(path, "wb") as f:
+            pickle.dump(self.state_dict(), f)
+
+    @staticmethod
+    def load(path, venv):
+        with open(path, "rb") as f:
+            sd = pickle.load(f)
+        vn = VecNormalize(venv)
+        vn.load_state_dict(sd)
+        return vn
+
+    def close(self):
+        self.venv.close()

@@ -1,0 +1,119 @@
+"""GPU: device VecNormalize against a numpy restatement of SB3's semantics, ResidualLoss against numpy,
+checkpoint round trips."""
+import numpy as np
+import pytest
+
+import sdc_gym_b200
+from sdc_gym_b200 import _lib
+from sdc_gym_b200.collocation import collocation_matrix
+from sdc_gym_b200.precond import fixed_preconditioner, num_actions, qdmat_from_output
+
+pytestmark = pytest.mark.gpu
+KW = dict(M=5, dt=1.0, restol=1e-10, lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0],
+          blas_variant=_lib.BLAS_SKYLAKEX)
+
+
+class NumpyRMS:  # stable_baselines3.common.running_mean_std.RunningMeanStd, restated
+    def __init__(self, shape):
+        self.mean, self.var, self.count = np.zeros(shape), np.ones(shape), 1e-4
+
+    def update(self, x):
+        bm, bv, bc = x.mean(0), x.var(0), x.shape[0]
+        delta = bm - self.mean
+        tot = self.count + bc
+        m2 = self.var * self.count + bv * bc + np.square(delta) * self.count * bc / tot
+        self.mean, self.var, self.count = self.mean + delta * bc / tot, m2 / tot, tot
+
+
+def planes_of(obs):  # (N, 2, M) complex -> (N, 4M) real in plane order
+    return obs.reshape(obs.shape[0], -1).view(np.float64)
+
+
+def test_vec_normalize_matches_sb3_semantics():
+    n = 4096
+    rng = np.random.default_rng(0)
+    raw = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=3, reward_iteration_only=False, **KW)
+    env = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=3, reward_iteration_only=False, **KW),
+                                    gamma=0.97)
+    obs_rms, ret_rms, returns = NumpyRMS(20), NumpyRMS(()), np.zeros(n)
+    o_raw = raw.reset()
+    o = env.reset()
+    obs_rms.update(planes_of(o_raw))
+    want = np.clip((planes_of(o_raw) - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
+    assert np.allclose(planes_of(o), want, rtol=1e-11, atol=1e-12)
+    x = np.diag(fixed_preconditioner("min", 5))
+    for s in range(12):
+        act = 2 * (x[None] + rng.uniform(-0.1, 0.1, (n, 5))) - 1
+        o_raw, r_raw, d_raw, i_raw = raw.step(act)
+        o, r, d, infos = env.step(act)
+        assert np.array_equal(d, d_raw)
+        obs_rms.update(planes_of(o_raw))
+        want = np.clip((planes_of(o_raw) - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
+        assert np.allclose(planes_of(o), want, rtol=1e-10, atol=1e-11), f"step {s}"
+        returns = returns * 0.97 + r_raw
+        ret_rms.update(returns)
+        want_r = np.clip(r_raw / np.sqrt(ret_rms.var + 1e-8), -10, 10)
+        assert np.allclose(r, want_r, rtol=1e-10, atol=1e-12), f"step {s} reward"
+        returns[d_raw] = 0
+        assert np.allclose(env.get_original_reward(), r_raw)
+        if d.any():
+            k = int(np.nonzero(d)[0][0])
+            t_raw = i_raw[k]["terminal_observation"]
+            t = infos[k]["terminal_observation"]
+            want_t = np.clip((planes_of(t_raw[None]) - obs_rms.mean) / np.sqrt(obs_rms.var + 1e-8), -10, 10)
+            assert np.allclose(planes_of(t[None]), want_t, rtol=1e-10, atol=1e-11)
+    assert abs(env.obs_rms.count - obs_rms.count) < 1e-6
+    assert np.allclose(env.obs_rms.mean.cpu().numpy(), obs_rms.mean, rtol=1e-11, atol=1e-13)
+    assert np.allclose(env.ret_rms.var.cpu().numpy(), ret_rms.var, rtol=1e-10)
+    assert np.allclose(env.normalize_obs(o_raw[:3]).reshape(3, -1).view(np.float64), want[:3], rtol=1e-10, atol=1e-11)
+    # frozen statistics + checkpoint round trip
+    sd = env.state_dict()
+    env2 = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=3, **KW), training=False)
+    env2.load_state_dict(sd)
+    assert np.array_equal(env2.obs_rms.var.cpu().numpy(), env.obs_rms.var.cpu().numpy())
+    o2 = env2.reset()
+    assert abs(env2.obs_rms.count - env.obs_rms.count) < 1e-9  # not training: untouched
+
+
+def test_env_state_dict_round_trip():
+    n = 1000
+    a = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=4, **KW)
+    a.reset()
+    act = np.random.default_rng(1).uniform(-1, 1, (n, 5))
+    a.step(act)
+    sd = a.state_dict()
+    b = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=99, **KW)
+    b.load_state_dict(sd)
+    oa, ra, da, ia = a.step(act)
+    ob, rb, db, ib = b.step(act)
+    assert np.array_equal(oa.view(np.float64), ob.view(np.float64), equal_nan=True) and np.array_equal(ra, rb)
+    assert np.array_equal(ia.niter, ib.niter) and np.array_equal(ia.lam, ib.lam)
+
+
+@pytest.mark.parametrize("prec_type", ["diag", "lower_tri", "strictly_lower_tri"])
+def test_residual_loss_against_numpy(prec_type):
+    from sdc_gym_b200.loss import ResidualLoss
+    M, B = 5, 3000
+    rng = np.random.default_rng(2)
+    Q = collocation_matrix(M)
+    A = num_actions(M, prec_type)
+    lam = rng.uniform(-100, 0, B) + 1j * rng.uniform(-10, 0, B)
+    out = rng.uniform(0, 0.3, (B, A)) + 1j * rng.uniform(-0.05, 0.05, (B, A))
+    u0 = rng.uniform(0, 1, (B, M)) + 1j * rng.uniform(0, 1, (B, M))
+    u = rng.uniform(0, 1, (B, M)) + 1j * rng.uniform(0, 1, (B, M))
+    Cs = np.eye(M)[None] - lam[:, None, None] * Q[None]
+    res = u0 - np.einsum("bij,bj->bi", Cs, u)
+    loss = ResidualLoss(M, 1.0, prec_type)
+    for C_arg in (Cs, None):
+        val, u_new, r_new = loss(lam.reshape(-1, 1), out, C_arg, u0, u, res)
+        ref_u, ref_r = np.empty_like(u), np.empty_like(u)
+        for b in range(B):
+            Qd = qdmat_from_output(out[b], M, prec_type)
+            Pinv = np.linalg.inv(np.eye(M) - lam[b] * Qd)
+            ref_u[b] = u[b] + Pinv @ res[b]
+            ref_r[b] = u0[b] - Cs[b] @ ref_u[b]
+        scale = np.abs(ref_u).max(axis=1, keepdims=True) * np.abs(lam)[:, None] + 1
+        assert np.all(np.abs(u_new.cpu().numpy() - ref_u) <= 1e-12 * scale)
+        assert np.all(np.abs(r_new.cpu().numpy() - ref_r) <= 1e-11 * scale)
+        ref_loss = np.abs(ref_r).max(axis=1).mean()
+        assert abs(float(val) - ref_loss) <= 1e-10 * ref_loss
