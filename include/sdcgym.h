@@ -116,7 +116,7 @@ typedef struct sdcgym_step_io {
     uint8_t* flags;        /* [N] SDCGYM_FLAG_* */
     double* info_residual; /* [N]  info['residual'] */
     int32_t* info_niter;   /* [N]  info['niter'] */
-    double* info_lam;      /* [2][ld] info['lam'] (the lambda the step ran with) */
+    double* info_lam;      /* [N][2] info['lam'] (the lambda the step ran with), interleaved complex128 */
     double* terminal_obs;  /* [4M][ld] state at episode end; written for envs whose DONE flag is set */
     double* old_states;    /* collect_states: (N, 2M, max_iters) complex128, env-major (reference layout) or NULL */
 } sdcgym_step_io;

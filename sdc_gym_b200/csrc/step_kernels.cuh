@@ -484,8 +484,8 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
     if (p.info_res) p.info_res[i] = nr;
     if (p.info_niter) p.info_niter[i] = it;
     if (p.info_lam) {
-        p.info_lam[i] = lr;
-        p.info_lam[ld + i] = li;
+        p.info_lam[2 * i] = lr;  // interleaved complex128, directly viewable by the host layer
+        p.info_lam[2 * i + 1] = li;
     }
     if (KIND == SDCGYM_ENV_STEP && p.old_states && it < p.max_iters)
         store_column<M>(p.old_states, i, p.max_iters, it, ur, ui, rr, ri);

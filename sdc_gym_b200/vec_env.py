@@ -87,6 +87,17 @@ class LazyInfos(Sequence):
         return d
 
 
+class _TruncatedKey:
+    """``'TimeLimit.truncated' in info`` per env: gym's TimeLimit adds the key once the episode has run
+    ``max_episode_steps`` steps (always for sdc-v0, at niter >= 50 for sdc-v1).  Evaluated lazily."""
+
+    def __init__(self, niter, max_steps):
+        self._niter, self._max = niter, max_steps
+
+    def __getitem__(self, i):
+        return bool(self._niter[i] >= self._max)
+
+
 class _EnvProxy:
     """``vec_env.envs[i]``: attribute view of one env of the batch (reads go through a cached host snapshot)."""
 
@@ -243,7 +254,7 @@ class SDCVecEnv:
             self.flags = torch.zeros(self.ld, dtype=torch.uint8, device=dev)
             self.info_residual = torch.zeros(self.ld, dtype=f64, device=dev)
             self.info_niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
-            self.info_lam = torch.zeros((2, self.ld), dtype=f64, device=dev)
+            self.info_lam = torch.zeros((self.ld, 2), dtype=f64, device=dev)
             self.terminal = torch.zeros((4 * self.M, self.ld), dtype=f64, device=dev)
             self.obs_aos = torch.zeros((N, 2, self.M, 2), dtype=f64, device=dev)
             a_w = max(1, self._kernel_n_act) * (2 if free_action_space else 1)
@@ -409,7 +420,7 @@ class SDCVecEnv:
         io.flags = self.flags.data_ptr() + start
         io.info_residual = self.info_residual.data_ptr() + 8 * start
         io.info_niter = self.info_niter.data_ptr() + 4 * start
-        io.info_lam = self.info_lam.data_ptr() + 8 * start
+        io.info_lam = self.info_lam.data_ptr() + 16 * start
         io.terminal_obs = (self.terminal.data_ptr() + 8 * start) if want_terminal else None
         io.old_states = (self.old_states.data_ptr() + 8 * start * 2 * self.M * self.max_iters * 2
                          if self.old_states is not None else None)
@@ -449,7 +460,8 @@ class SDCVecEnv:
             self._reset_done_envs()
         self._invalidate()
         return dict(reward=self.reward[:N], flags=self.flags[:N], niter=self.info_niter[:N],
-                    residual=self.info_residual[:N], lam=self.info_lam[:, :N], terminal=self.terminal[:, :N])
+                    residual=self.info_residual[:N], lam=torch.view_as_complex(self.info_lam)[:N],
+                    terminal=self.terminal[:, :N])
 
     def _reset_done_envs(self):
         # collect_states: the kernel leaves finished envs alone; snapshot their buffers, then masked reset
@@ -469,24 +481,47 @@ class SDCVecEnv:
             a_w = self.action_dev.shape[1]
             self._host = dict(
                 action=torch.zeros((N, a_w), dtype=torch.float64, **pin),
+                actions=[],
                 obs=torch.zeros((N, 2, M, 2), dtype=torch.float64, **pin),
                 reward=torch.zeros(N, dtype=torch.float64, **pin),
                 flags=torch.zeros(N, dtype=torch.uint8, **pin),
                 niter=torch.zeros(N, dtype=torch.int32, **pin),
                 residual=torch.zeros(N, dtype=torch.float64, **pin),
-                lam=torch.zeros((2, N), dtype=torch.float64, **pin),
+                lam=torch.zeros((N, 2), dtype=torch.float64, **pin),
             )
+            self._host["actions"].append(self._host["action"])
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         return self._host
 
-    def pinned_action_buffer(self):
-        """Page-locked numpy view (N, A) [(N, A) complex128 with free_action_space] that ``step`` uploads
-        from without an intermediate copy: write the actions here and pass this very array to ``step``."""
-        h = self._ensure_host()["action"]
-        a = h.numpy()
+    def pinned_action_buffer(self, index=0):
+        """Page-locked numpy view (N, A) [(N, A) complex128 with free_action_space] that ``step`` uploads from
+        without an intermediate copy: write the actions here and pass this very array to ``step``.  Two buffers
+        (index 0 / 1) exist so a caller can fill one while the other is in flight."""
+        host = self._ensure_host()
+        while len(host["actions"]) <= index:
+            host["actions"].append(_torch().zeros_like(host["action"]).pin_memory())
+        a = host["actions"][index].numpy()
         if self.free_action_space:
             return a.view(np.complex128)
         return a
+
+    def _stage_actions(self, host, actions):
+        """Return the pinned tensor holding ``actions`` (uploading from the caller's array when it already is one
+        of ours, else copying it into staging buffer 0)."""
+        if self.free_action_space:
+            a = np.ascontiguousarray(actions, dtype=np.complex128).reshape(self.num_envs, self._kernel_n_act)
+            a = a.view(np.float64)
+        else:
+            a = np.asarray(actions)
+            if np.iscomplexobj(a):
+                raise TypeError("complex actions need free_action_space=True")
+            a = np.asarray(a, dtype=np.float64).reshape(self.num_envs, self._kernel_n_act)
+        ptr = a.__array_interface__["data"][0]
+        for t in host["actions"]:
+            if t.data_ptr() == ptr and a.flags.c_contiguous:
+                return t
+        np.copyto(host["actions"][0].numpy(), a)
+        return host["actions"][0]
 
     def step_async(self, actions):
         self._pending = actions
@@ -506,22 +541,11 @@ class SDCVecEnv:
         N, M = self.num_envs, self.M
         host = self._ensure_host()
         # ---- stage actions in pinned memory (no-op when the caller wrote into pinned_action_buffer()) ----
-        if self._kernel_n_act > 0:
-            a = np.asarray(actions)
-            if self.free_action_space:
-                a = np.ascontiguousarray(a, dtype=np.complex128).reshape(N, self._kernel_n_act)
-                stage = host["action"].numpy().view(np.complex128)
-            else:
-                if np.iscomplexobj(a):
-                    raise TypeError("complex actions need free_action_space=True")
-                a = np.asarray(a, dtype=np.float64).reshape(N, self._kernel_n_act)
-                stage = host["action"].numpy()
-            if not np.shares_memory(a, stage):
-                np.copyto(stage, a)
+        src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
         if self.collect_states:
-            return self._step_collect_states(host)
+            return self._step_collect_states(host, src)
         # ---- chunked pipeline: H2D(actions) | kernel + export | D2H(results) on three streams ----
-        chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(16, N // 65536))
+        chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(8, N // 131072))
         bounds = [(N * c // chunks // 32 * 32 if c < chunks else N) for c in range(chunks + 1)]
         bounds[0] = 0
         main = torch.cuda.current_stream(self.device)
@@ -535,7 +559,7 @@ class SDCVecEnv:
                 continue
             if self._kernel_n_act > 0:
                 with torch.cuda.stream(s_in):
-                    self.action_dev[lo:hi].copy_(host["action"][lo:hi], non_blocking=True)
+                    self.action_dev[lo:hi].copy_(src[lo:hi], non_blocking=True)
                 main.wait_stream(s_in)
             self._launch_step(self.action_dev.data_ptr() + 8 * lo * a_w if self._kernel_n_act else None,
                               a_w, 2 if self.free_action_space else 1, start=lo, count=hi - lo)
@@ -547,7 +571,7 @@ class SDCVecEnv:
                 host["flags"][lo:hi].copy_(self.flags[lo:hi], non_blocking=True)
                 host["niter"][lo:hi].copy_(self.info_niter[lo:hi], non_blocking=True)
                 host["residual"][lo:hi].copy_(self.info_residual[lo:hi], non_blocking=True)
-                host["lam"][:, lo:hi].copy_(self.info_lam[:, lo:hi], non_blocking=True)
+                host["lam"][lo:hi].copy_(self.info_lam[lo:hi], non_blocking=True)
         s_out.synchronize()
         main.wait_stream(s_out)
         self._invalidate()
@@ -558,14 +582,13 @@ class SDCVecEnv:
         cp = (lambda x: x) if self.reuse_buffers else np.copy
         obs = cp(host["obs"].numpy().view(np.complex128).reshape(N, 2, self.M))
         rewards = cp(host["reward"].numpy())
-        flags = host["flags"].numpy()
-        dones = (flags & _lib.FLAG_DONE).astype(bool)
-        lam = host["lam"].numpy()
+        flags = cp(host["flags"].numpy())
+        dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
         niter = cp(host["niter"].numpy())
-        truncated_key = niter >= MAX_EPISODE_STEPS[self.envname] if self.envname == "sdc-v1" else np.ones(N, bool)
-        infos = LazyInfos(niter, cp(host["residual"].numpy()), lam[0] + 1j * lam[1], dones, truncated_key,
-                          self._fetch_terminal)
-        infos.flags = cp(flags)
+        lam = cp(host["lam"].numpy()).view(np.complex128).reshape(N)
+        truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
+        infos = LazyInfos(niter, cp(host["residual"].numpy()), lam, dones, truncated_key, self._fetch_terminal)
+        infos.flags = flags
         return obs, rewards, dones, infos
 
     def _fetch_terminal(self):
@@ -579,12 +602,12 @@ class SDCVecEnv:
         self.obs_aos.copy_(keep)
         return out
 
-    def _step_collect_states(self, host):
+    def _step_collect_states(self, host, src):
         torch = _torch()
         N = self.num_envs
         a_w = self.action_dev.shape[1]
         if self._kernel_n_act > 0:
-            self.action_dev.copy_(host["action"], non_blocking=True)
+            self.action_dev.copy_(src, non_blocking=True)
         self._launch_step(self.action_dev.data_ptr() if self._kernel_n_act else None, a_w,
                           2 if self.free_action_space else 1)
         if self.autoreset:
@@ -593,10 +616,10 @@ class SDCVecEnv:
         obs = torch.view_as_complex(self.old_states).cpu().numpy()
         flags = self.flags[:N].cpu().numpy()
         dones = (flags & _lib.FLAG_DONE).astype(bool)
-        lam = self.info_lam[:, :N].cpu().numpy()
+        lam = torch.view_as_complex(self.info_lam)[:N].cpu().numpy()
         niter = self.info_niter[:N].cpu().numpy()
-        truncated_key = niter >= MAX_EPISODE_STEPS[self.envname] if self.envname == "sdc-v1" else np.ones(N, bool)
-        infos = LazyInfos(niter, self.info_residual[:N].cpu().numpy(), lam[0] + 1j * lam[1], dones, truncated_key,
+        truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
+        infos = LazyInfos(niter, self.info_residual[:N].cpu().numpy(), lam, dones, truncated_key,
                           self._fetch_terminal)
         infos.flags = flags
         return obs, self.reward[:N].cpu().numpy(), dones, infos

@@ -171,15 +171,15 @@ class VecNormalize:
         self.old_reward = out["raw_reward"]
         if v.output == "torch":
             return obs, out["reward"], (out["flags"] & 1).bool(), out
-        from .vec_env import MAX_EPISODE_STEPS, LazyInfos
+        from .vec_env import MAX_EPISODE_STEPS, LazyInfos, _TruncatedKey
 
         flags = out["flags"].cpu().numpy()
         dones = (flags & 1).astype(bool)
         niter = out["niter"].cpu().numpy()
         lam = out["lam"].cpu().numpy()
-        trunc = niter >= MAX_EPISODE_STEPS[v.envname] if v.envname == "sdc-v1" else np.ones(N, bool)
+        trunc = _TruncatedKey(niter, MAX_EPISODE_STEPS[v.envname])
         term_planes = self.norm_terminal if self.norm_obs else v.terminal
-        infos = LazyInfos(niter, out["residual"].cpu().numpy(), lam[0] + 1j * lam[1], dones, trunc,
+        infos = LazyInfos(niter, out["residual"].cpu().numpy(), lam, dones, trunc,
                           lambda: self._terminal_host(term_planes))
         infos.flags = flags
         return obs, out["reward"].cpu().numpy(), dones, infos

@@ -89,7 +89,7 @@ class ShimBatch:
         self.flags = np.zeros(ld, np.uint8)
         self.info_res = np.zeros(ld)
         self.info_niter = np.zeros(ld, np.int32)
-        self.info_lam = np.zeros((2, ld))
+        self.info_lam = np.zeros((ld, 2))
         self.term = np.zeros((4 * M, ld))
         self.old_states = np.zeros((n, 2 * M, 50), np.complex128) if collect else None
 
@@ -143,7 +143,7 @@ class ShimBatch:
         tu, tr = self.planes_to_obs(self.term)
         return dict(u=u, r=r, term_u=tu, term_r=tr, reward=self.reward[:n].copy(), done=(f & 1) != 0, conv=(f & 2) != 0,
                     err=(f & 4) != 0, niter=self.info_niter[:n].copy(), residual=self.info_res[:n].copy(),
-                    lam=self.info_lam[0, :n] + 1j * self.info_lam[1, :n])
+                    lam=self.info_lam[:n].copy().view(np.complex128).reshape(n))
 
 
 def spectral_radius(M, prec_type, lam, qd, *, dt=1.0, Q=None, Qd_fixed=None, grid=None):
