@@ -58,8 +58,10 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         }
     }
 #endif
-    step_kernel<kM, KIND, V, DENSE, (DENSE ? kHoldDense : kHoldDiag),
-                (DENSE ? HoldPolicy<kM>::dense_minb : HoldPolicy<kM>::diag_minb)><<<grid, kBlock, 0, s>>>(p);
+    constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
+    constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
+    constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);
+    step_kernel<kM, KIND, V, DENSE, hold, minb><<<grid, kBlock, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -90,7 +92,14 @@ extern "C" int SDCGYM_CAT(sdcgym_launch_step_m, SDCGYM_M)(const sdcgym_env_desc*
     fill_step_io<kM>(p, io);
     if (p.N <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool dense = d->prec_type != SDCGYM_PREC_DIAG;
+    bool dense = d->prec_type != SDCGYM_PREC_DIAG;
+    if (d->prec_type == SDCGYM_PREC_FIXED) {  // a fixed diagonal matrix takes the diagonal fast path
+        bool diagonal = true;
+        for (int r = 0; r < kM; r++)
+            for (int c = 0; c < kM; c++)
+                if (r != c && d->Qd_fixed[r * kM + c] != 0.0) diagonal = false;
+        dense = !diagonal;
+    }
     const bool full = d->env_kind == SDCGYM_ENV_FULL;
     const bool skx = d->blas_variant == SDCGYM_BLAS_SKYLAKEX;
     cudaError_t e;

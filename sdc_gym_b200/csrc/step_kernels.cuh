@@ -11,11 +11,13 @@
 #pragma once
 #include "../../include/sdcgym.h"
 #include "exact_math.cuh"
+#include "exact_inv_reg.cuh"
 #include "philox.cuh"
 
 namespace sdcgym {
 
 constexpr int kBlock = 128;
+constexpr int kRegInvMaxM = 5;  // largest M whose exact inverse is computed in registers (exact_inv_reg.cuh)
 
 template <int M>
 struct StepParams {
@@ -268,7 +270,12 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
 #pragma unroll
         for (int k = 0; k < M; k++) {
             cplx zq;
-            if (p.is_complex) {
+            if (p.prec_type == SDCGYM_PREC_FIXED) {
+                // fixed *diagonal* Q_delta (prec='min' / 'zeros'): the dense inverse of a diagonal matrix is the
+                // diagonal of reciprocals (bit-identical, tests/test_blas_fingerprint.py), so these run here
+                const double d = p.Qd[k * M + k];
+                zq = cplx{dmul(zr, d), dmul(zi, d)};
+            } else if (p.is_complex) {
                 cplx d{ld_ro(p.action + i * p.a_es + k * p.a_cs), ld_ro(p.action + i * p.a_es + k * p.a_cs + 1)};
                 zq = cmul_np(cplx{zr, zi}, d);
             } else {
@@ -282,44 +289,69 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
             Pi[k] = inv.im;
         }
     } else {
-        cplx A[M * M], B[M * M];  // column-major work arrays (local memory)
-#pragma unroll 1
-        for (int r = 0, k = 0; r < M; r++)
-#pragma unroll 1
-            for (int c = 0; c < M; c++) {
-                cplx d{0.0, 0.0};
-                bool take;
-                switch (p.prec_type) {
-                case SDCGYM_PREC_LOWER_DIAG: take = (r == c + 1); break;
-                case SDCGYM_PREC_LOWER_TRI: take = (c <= r); break;
-                case SDCGYM_PREC_STRICTLY_LOWER_TRI: take = (c < r); break;
-                case SDCGYM_PREC_DIAG: take = (c == r); break;
-                default: take = false; break;
+        // P = eye(M) - (lam*dt)*Qd, column-major; Qd from the action layout (dp_playground.py:194-207) or fixed
+        auto qd_entry = [&](int r, int c, int k) {
+            cplx d{0.0, 0.0};
+            if (p.prec_type == SDCGYM_PREC_FIXED) {
+                d.re = p.Qd[r * M + c];
+            } else if (k >= 0) {
+                if (p.is_complex) {
+                    d.re = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                    d.im = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
+                } else {
+                    const double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                    d.re = a;
+                    if (p.do_scale) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
                 }
-                if (p.prec_type == SDCGYM_PREC_FIXED) {
-                    d.re = p.Qd[r * M + c];
-                } else if (take) {
-                    if (p.is_complex) {
-                        d.re = ld_ro(p.action + i * p.a_es + k * p.a_cs);
-                        d.im = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
-                    } else {
-                        double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
-                        d.re = a;
-                        if (p.do_scale) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
-                    }
-                    k++;
+            }
+            return d;
+        };
+        // index of entry (r, c) in the action vector for the run-time layout, -1 if the entry is structurally zero
+        auto act_index = [&](int r, int c) {
+            switch (p.prec_type) {
+            case SDCGYM_PREC_LOWER_DIAG: return (r == c + 1) ? c : -1;
+            case SDCGYM_PREC_LOWER_TRI: return (c <= r) ? r * (r + 1) / 2 + c : -1;
+            case SDCGYM_PREC_STRICTLY_LOWER_TRI: return (c < r) ? r * (r - 1) / 2 + c : -1;
+            case SDCGYM_PREC_DIAG: return (c == r) ? r : -1;
+            default: return -1;
+            }
+        };
+        if constexpr (M <= kRegInvMaxM) {
+            double Ar[M * M], Ai[M * M], Br[M * M], Bi[M * M];
+#pragma unroll
+            for (int r = 0; r < M; r++)
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    Ar[r + c * M] = dsub((r == c) ? 1.0 : 0.0, zq.re);
+                    Ai[r + c * M] = dsub(0.0, zq.im);
                 }
-                cplx zq = cmul_np(cplx{zr, zi}, d);
-                A[r + c * M] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
-            }
-        cinv_exact<M, V>(A, B);
+            cinv_exact_reg<M, V>(Ar, Ai, Br, Bi);
 #pragma unroll
-        for (int r = 0; r < M; r++)
+            for (int r = 0; r < M; r++)
 #pragma unroll
-            for (int c = 0; c < M; c++) {
-                Pr[r * M + c] = B[r + c * M].re;
-                Pi[r * M + c] = B[r + c * M].im;
-            }
+                for (int c = 0; c < M; c++) {
+                    Pr[DENSE ? r * M + c : 0] = Br[r + c * M];
+                    Pi[DENSE ? r * M + c : 0] = Bi[r + c * M];
+                }
+        } else {
+            cplx A[M * M], B[M * M];  // column-major work arrays (local memory)
+#pragma unroll 1
+            for (int r = 0; r < M; r++)
+#pragma unroll 1
+                for (int c = 0; c < M; c++) {
+                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    A[r + c * M] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
+                }
+            cinv_exact<M, V>(A, B);
+#pragma unroll
+            for (int r = 0; r < M; r++)
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    Pr[DENSE ? r * M + c : 0] = B[r + c * M].re;
+                    Pi[DENSE ? r * M + c : 0] = B[r + c * M].im;
+                }
+        }
     }
 
     // ---- system matrix (optionally register resident) ----

@@ -76,6 +76,9 @@ struct HoldPolicy {
     static constexpr int diag_minb = (M <= 5) ? 3 : 2;
     static constexpr int dense = (M <= 3) ? 2 : 0;
     static constexpr int dense_minb = 2;
+    // sdc-v1 runs a single sweep per launch and is memory bound: nothing is worth holding, occupancy is
+    static constexpr int step = 0;
+    static constexpr int step_minb = (M <= 5) ? 4 : 2;
 };
 
 }  // namespace sdcgym

@@ -48,7 +48,15 @@ static int step_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym
     StepParams<M> p;
     fill_params<M>(p, d, st);
     fill_step_io<M>(p, io);
-    const bool dense = d->prec_type != SDCGYM_PREC_DIAG, full = d->env_kind == SDCGYM_ENV_FULL;
+    bool dense = d->prec_type != SDCGYM_PREC_DIAG;
+    const bool full = d->env_kind == SDCGYM_ENV_FULL;
+    if (d->prec_type == SDCGYM_PREC_FIXED) {
+        bool diagonal = true;
+        for (int r = 0; r < M; r++)
+            for (int c = 0; c < M; c++)
+                if (r != c && d->Qd_fixed[r * M + c] != 0.0) diagonal = false;
+        dense = !diagonal;
+    }
     constexpr int HD = HoldPolicy<M>::diag, HS = HoldPolicy<M>::dense;
     // emulate whole thread blocks so the i >= N clamping path is exercised too
     const int64_t nthreads = (p.N + kBlock - 1) / kBlock * kBlock;
@@ -122,6 +130,22 @@ extern "C" int shim_spectral_radius(const sdcgym_rho_desc* d, int64_t N, const d
 // ---- direct access to the exact inverse template (row-major complex in/out) ----
 template <int M>
 static void cinv_m(const double* P, double* out, int variant) {
+    if (variant >= 2) {  // register-resident formulation (exact_inv_reg.cuh)
+        double Ar[M * M], Ai[M * M], Br[M * M], Bi[M * M];
+        for (int r = 0; r < M; r++)
+            for (int c = 0; c < M; c++) {
+                Ar[r + c * M] = P[(r * M + c) * 2];
+                Ai[r + c * M] = P[(r * M + c) * 2 + 1];
+            }
+        if (variant == 2) cinv_exact_reg<M, 0>(Ar, Ai, Br, Bi);
+        else cinv_exact_reg<M, 1>(Ar, Ai, Br, Bi);
+        for (int r = 0; r < M; r++)
+            for (int c = 0; c < M; c++) {
+                out[(r * M + c) * 2] = Br[r + c * M];
+                out[(r * M + c) * 2 + 1] = Bi[r + c * M];
+            }
+        return;
+    }
     cplx A[M * M], B[M * M];
     for (int r = 0; r < M; r++)
         for (int c = 0; c < M; c++) A[r + c * M] = cplx{P[(r * M + c) * 2], P[(r * M + c) * 2 + 1]};
