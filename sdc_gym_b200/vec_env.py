@@ -274,7 +274,10 @@ class SDCVecEnv:
         d.prec_type = _lib.PREC_TYPES[self.prec_type]
         d.action_is_complex, d.do_scale = int(self.free_action_space), int(self.do_scale)
         d.max_iters = self.max_iters
-        d.reward_strategy = _lib.REWARD_STRATEGIES[self.reward_strategy]
+        # 'spectral_radius' (sdc_env.py:421-425) is composed from two kernels: the step runs with the cheapest
+        # in-kernel reward and `_apply_spectral_radius_reward` overwrites it with rho from the eigenvalue kernel
+        self._rho_reward = self.reward_strategy == "spectral_radius"
+        d.reward_strategy = _lib.REWARD_STRATEGIES["iteration_only" if self._rho_reward else self.reward_strategy]
         d.blas_variant = detect_blas_variant() if blas_variant is None else int(blas_variant)
         d.autoreset = int(self.autoreset and not self.collect_states)
         d.curriculum = int(lambda_real_interpolation_interval is not None)
@@ -456,12 +459,33 @@ class SDCVecEnv:
             self._keep = a
             ptr = a.data_ptr()
         self._launch_step(ptr, es, cs, want_terminal=want_terminal)
+        if self._rho_reward:
+            self._apply_spectral_radius_reward(actions if self._kernel_n_act else None)
         if self.collect_states and self.autoreset:
             self._reset_done_envs()
         self._invalidate()
         return dict(reward=self.reward[:N], flags=self.flags[:N], niter=self.info_niter[:N],
                     residual=self.info_residual[:N], lam=torch.view_as_complex(self.info_lam)[:N],
                     terminal=self.terminal[:, :N])
+
+    def _apply_spectral_radius_reward(self, actions_t):
+        """reward = rho(lam*dt*Pinv (Q - Qd)) for every env that did not err (reference reward_func :459-460)."""
+        torch = _torch()
+        from .loss import SpectralRadiusLoss
+
+        if getattr(self, "_rho_loss", None) is None:
+            self._rho_loss = SpectralRadiusLoss(self.M, self.dt, self.prec_type if self.prec is None else "diag",
+                                                prec=self.prec, Q=self.Q, device=self.device)
+        N = self.num_envs
+        lam = torch.view_as_complex(self.info_lam)[:N]
+        out = None
+        if self.prec is None:
+            out = actions_t
+            if not self.free_action_space and self.do_scale:
+                out = ((actions_t + 1.0) * 0.5).clamp(0.0, 1.0)  # _scale_action, sdc_env.py:125-132
+        rho = self._rho_loss.spectral_radii(lam, out)
+        err = (self.flags[:N] & _lib.FLAG_ERR).ne(0)
+        self.reward[:N] = torch.where(err, self.reward[:N], rho)
 
     def _reset_done_envs(self):
         # collect_states: the kernel leaves finished envs alone; snapshot their buffers, then masked reset
@@ -539,6 +563,8 @@ class SDCVecEnv:
             dones = (out["flags"] & _lib.FLAG_DONE).bool()
             return obs, out["reward"], dones, out
         N, M = self.num_envs, self.M
+        if self._rho_reward:
+            return self._step_simple(actions)
         host = self._ensure_host()
         # ---- stage actions in pinned memory (no-op when the caller wrote into pinned_action_buffer()) ----
         src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
@@ -576,6 +602,24 @@ class SDCVecEnv:
         main.wait_stream(s_out)
         self._invalidate()
         return self._host_outputs(host)
+
+    def _step_simple(self, actions):
+        """Unpipelined host step (rarely used configurations): upload, device step, download."""
+        torch = _torch()
+        N = self.num_envs
+        a = None
+        if self._kernel_n_act > 0:
+            arr = np.asarray(actions, dtype=np.complex128 if self.free_action_space else np.float64)
+            a = torch.as_tensor(np.ascontiguousarray(arr.reshape(N, self._kernel_n_act))).to(self.device)
+        out = self.step_tensor(a)
+        obs = self.observation_tensor().cpu().numpy()
+        flags = out["flags"].cpu().numpy()
+        dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
+        niter = out["niter"].cpu().numpy()
+        infos = LazyInfos(niter, out["residual"].cpu().numpy(), out["lam"].cpu().numpy(), dones,
+                          _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]), self._fetch_terminal)
+        infos.flags = flags
+        return obs, out["reward"].cpu().numpy(), dones, infos
 
     def _host_outputs(self, host):
         N = self.num_envs

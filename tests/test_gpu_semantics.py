@@ -268,3 +268,76 @@ def test_full_size_properties_one_million_envs():
     assert_same(res.cpu().numpy()[idx], o["resnorm"])
     term = out["terminal"].cpu().numpy()[:, idx]
     assert_same((term[0:10:2] + 1j * term[1:10:2]).T, u); assert_same((term[10::2] + 1j * term[11::2]).T, r)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 129, 1000])
+@pytest.mark.parametrize("M", [2, 9])
+def test_ragged_batch_sizes_and_extreme_M(n, M):
+    """empty, single-env and non-multiple-of-warp batches at the smallest / largest supported M"""
+    rng = np.random.default_rng(n + M)
+    Q = collocation_matrix(M)
+    env = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=1, autoreset=False, **{**KW, "M": M})
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+    obs = env.reset(lam=lam)
+    assert obs.shape == (n, 2, M)
+    act = rng.uniform(-0.6, -0.2, (n, M))
+    obs, rew, done, infos = env.step(act)
+    assert obs.shape == (n, 2, M) and rew.shape == (n,) and done.shape == (n,) and len(infos) == n
+    if n:
+        u, r = exact.reset(Q, 1.0, lam)
+        nit = np.zeros(n, np.int32)
+        o = exact.step("sdc-v0", Q, 1.0, lam, u, r, nit, r.copy(), act)
+        snap = env._snapshot()
+        assert_same(snap["obs"][:, 0], u); assert_same(snap["obs"][:, 1], r)
+        assert np.array_equal(infos.niter, nit) and done.all()
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        sdc_gym_b200.make("sdc-v0", num_envs=4, **{**KW, "M": 10})
+    with pytest.raises(NotImplementedError):
+        sdc_gym_b200.make("sdc-v0", num_envs=4, use_doubles=False, **KW)
+    with pytest.raises(NotImplementedError):
+        sdc_gym_b200.make("sdc-v0", num_envs=4, reward_strategy="nope", **KW)
+    env = sdc_gym_b200.make("sdc-v0", num_envs=4, **KW)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(np.zeros((4, 3)))
+    with pytest.raises(TypeError):
+        env.step(np.zeros((4, 5), np.complex128))
+
+
+def test_spectral_radius_reward_strategy():
+    n, M = 500, 5
+    rng = np.random.default_rng(12)
+    Q = collocation_matrix(M)
+    env = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=2, reward_strategy="spectral_radius", autoreset=False, **KW)
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+    env.reset(lam=lam)
+    act = good_actions(rng, n, spread=0.05)
+    _, rew, done, infos = env.step(act)
+    d = np.clip(0.5 * (act + 1), 0, 1)
+    for i in range(0, n, 7):
+        Qd = np.diag(d[i])
+        ref = max(abs(np.linalg.eigvals(lam[i] * np.linalg.inv(np.eye(M) - lam[i] * Qd).dot(Q - Qd))))
+        if infos.flags[i] & 4:
+            assert rew[i] == -0.1 * 51
+        else:
+            assert abs(rew[i] - ref) <= 1e-10 * ref
+
+
+def test_curriculum_lambda_interval():
+    """lambda_real_interpolation_interval (sdc_env.py:287-292): the lower real bound follows np.interp of the
+    episode count."""
+    n = 2000
+    env = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=9, lambda_real_interpolation_interval=[2, 6], **KW)
+    for ep in range(1, 9):
+        env.reset()
+        lam = np.array(env.get_attr("lam"))
+        lo = float(np.interp(ep, [2, 6], [0, -100]))
+        want = host_rng.lambda_stream(9, np.arange(n), ep - 1, (-100, 0), (-10, 0), re_lo_override=lo)
+        assert_same(lam, want, f"episode {ep}")
+        assert np.all(lam.real >= lo - 1e-12) and np.all(lam.real <= 0)
+    env.set_num_episodes(100)
+    env.reset()
+    assert np.array(env.get_attr("lam")).real.min() < -90

@@ -74,3 +74,37 @@ def test_v0_lower_tri_and_v1_rollout():
     _run("sdc-v0", 5, 600, prec_type="lower_tri", seed=8)
     _run("sdc-v1", 5, 300, mode="good", steps=50, strategy="residual_change", seed=9)
     _run("sdc-v1", 7, 200, prec="LU", steps=30, strategy="residual_change", seed=10)
+
+
+def test_philox_draws_curriculum_and_fused_autoreset_on_host():
+    """kernel templates on the host: lambda draws equal the numpy restatement (incl. the np.interp curriculum of
+    sdc_env.py:287-292), and the fused auto-reset leaves the reset state of the next lambda + terminal planes."""
+    from sdc_gym_b200 import rng as host_rng
+    n, M = 300, 5
+    Q = collocation_matrix(M)
+    d = host_shim.make_desc("sdc-v0", M, seed=17, env_offset=1000, autoreset=True, curriculum=(2, 6))
+    b = host_shim.ShimBatch(d, n)
+    rng = np.random.default_rng(0)
+    for ep in range(1, 5):
+        u, r = b.reset()
+        lo = float(np.interp(ep, [2, 6], [0, -100]))
+        lam = host_rng.lambda_stream(17, 1000 + np.arange(n), ep - 1, (-100, 0), (-10, 0), re_lo_override=lo)
+        assert_same(b.lam[0, :n] + 1j * b.lam[1, :n], lam, f"draw {ep}")
+        ou, orr = exact.reset(Q, 1.0, lam)
+        assert_same(u, ou); assert_same(r, orr)
+        assert np.all(b.episodes[:n] == ep)
+    # one fused step: terminal planes hold the solve, S the next episode
+    act = 2 * (np.diag(fixed_preconditioner("min", M))[None] + rng.uniform(-0.03, 0.03, (n, M))) - 1
+    out = b.step(act)
+    nit = np.zeros(n, np.int32)
+    o = exact.step("sdc-v0", Q, 1.0, lam, ou, orr, nit, orr.copy(), act)
+    assert_same(out["term_u"], ou); assert_same(out["term_r"], orr)
+    assert np.array_equal(out["niter"], nit) and out["done"].all()
+    assert_same(out["lam"], lam, "info lam = finished lambda")
+    lo = float(np.interp(5, [2, 6], [0, -100]))
+    lam2 = host_rng.lambda_stream(17, 1000 + np.arange(n), 4, (-100, 0), (-10, 0), re_lo_override=lo)
+    assert_same(b.lam[0, :n] + 1j * b.lam[1, :n], lam2)
+    nu, nr = exact.reset(Q, 1.0, lam2)
+    assert_same(out["u"], nu); assert_same(out["r"], nr)
+    assert np.all(b.episodes[:n] == 5) and np.all(b.niter[:n] == 0)
+    assert_same(b.resnorm[:n], np.abs(nr).max(axis=1))
