@@ -53,6 +53,23 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         SDCGYM_TV(15, 1, 2, 256)
         SDCGYM_TV(16, 0, 2, 256)
         SDCGYM_TV(17, 1, 4, 96)
+#define SDCGYM_TVS(n, HOLD, MINB, BLK)                                                                       \
+        case n:                                                                                              \
+            cudaFuncSetAttribute(step_kernel<kM, KIND, V, DENSE, HOLD, MINB, BLK>,                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_kernel_smem_bytes<kM, HOLD, BLK>()); \
+            step_kernel<kM, KIND, V, DENSE, HOLD, MINB, BLK><<<(unsigned)((p.N + BLK - 1) / BLK), BLK,        \
+                                                               step_kernel_smem_bytes<kM, HOLD, BLK>(), s>>>(p); \
+            return cudaGetLastError();
+        SDCGYM_TVS(20, 3, 3, 128)
+        SDCGYM_TVS(21, 3, 4, 128)
+        SDCGYM_TVS(22, 3, 6, 64)
+        SDCGYM_TVS(23, 3, 2, 128)
+        SDCGYM_TVS(24, 4, 4, 128)
+        SDCGYM_TVS(25, 4, 3, 128)
+        SDCGYM_TVS(26, 4, 8, 64)
+        SDCGYM_TVS(27, 4, 5, 128)
+        SDCGYM_TVS(28, 4, 5, 96)
+#undef SDCGYM_TVS
 #undef SDCGYM_TV
         default: break;
         }
@@ -61,7 +78,18 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
     constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);
-    step_kernel<kM, KIND, V, DENSE, hold, minb><<<grid, kBlock, 0, s>>>(p);
+    constexpr int block = (!DENSE && !kStep) ? HoldPolicy<kM>::diag_block : kBlock;
+    constexpr size_t smem = step_kernel_smem_bytes<kM, hold, block>();
+    auto kernel = step_kernel<kM, KIND, V, DENSE, hold, minb, block>;
+    if (smem > 48 * 1024) {
+        static bool configured = false;  // per instantiation; one host thread per GPU drives the library
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+    }
+    kernel<<<(unsigned)((p.N + block - 1) / block), block, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -246,7 +246,9 @@ SDCGYM_HD HiBand make_band(double t) {
 // =====================================================================================================
 // step kernel.  KIND: SDCGYM_ENV_FULL / SDCGYM_ENV_STEP.  DENSE: Pinv is a full M x M matrix obtained by
 // the exact np.linalg.inv emulation (any non-diagonal Q_delta), otherwise Pinv is diagonal (prec=None,
-// diag actions).  HOLD: 2 = keep Re and Im of C in registers, 1 = only Re, 0 = recompute z*q on use.
+// diag actions).  HOLD: 2 = keep Re and Im of C in registers, 1 = only Re (Im re-derived from the constant bank),
+// 0 = recompute z*q on use, 3 = Re in registers and Im in shared memory (`side`, element k of this thread at
+// side[k * side_stride]; the LDS run on the memory pipe beside the saturated FP64 pipe).
 // =====================================================================================================
 #ifdef __CUDA_ARCH__
 #define SDCGYM_WARP_ANY(x) __any_sync(0xffffffffu, (x))
@@ -255,7 +257,7 @@ SDCGYM_HD HiBand make_band(double t) {
 #endif
 
 template <int M, int KIND, int V, bool DENSE, int HOLD>
-SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
+SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1) {
     const bool valid = tid < p.N;
     const int64_t i = valid ? tid : p.N - 1;
     const int64_t ld = p.ld;
@@ -355,7 +357,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
     }
 
     // ---- system matrix (optionally register resident) ----
-    constexpr int NCR = (HOLD >= 1) ? M * M : 1, NCI = (HOLD >= 2) ? M * M : 1;
+    constexpr int NCR = (HOLD >= 1 && HOLD <= 3) ? M * M : 1, NCI = (HOLD == 2) ? M * M : 1;
     double Cr[NCR], Ci[NCI];
     if (HOLD >= 1) {
 #pragma unroll
@@ -363,8 +365,11 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
 #pragma unroll
             for (int c = 0; c < M; c++) {
                 double q = p.Q[r * M + c];
-                Cr[(HOLD >= 1) ? r * M + c : 0] = (r == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
-                if (HOLD >= 2) Ci[(HOLD >= 2) ? r * M + c : 0] = -dmul(zi, q);
+                const double crv = (r == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
+                if (HOLD <= 3) Cr[(HOLD >= 1 && HOLD <= 3) ? r * M + c : 0] = crv;
+                if (HOLD == 4) side[(M * M + r * M + c) * side_stride] = crv;
+                if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
+                if (HOLD >= 3) side[(r * M + c) * side_stride] = -dmul(zi, q);
             }
     }
 
@@ -391,8 +396,11 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
         // sweep; the empty asm keeps the compiler from hoisting those products back out of the loop (which
         // would turn them into spills).
         double zr_s = zr, zi_s = zi;
+        // volatile: the side store is loop invariant, and a hoisted load is a register again
+        const volatile double* vside = side;
+        (void)vside;
 #ifdef __CUDA_ARCH__
-        if (HOLD < 2) asm volatile("" : "+d"(zr_s), "+d"(zi_s));
+        if (HOLD < 2) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
 #endif
         double dr[M], di[M];
 #pragma unroll
@@ -420,9 +428,11 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid) {
 #pragma unroll
             for (int c = 0; c < M; c++) {
                 double q = p.Q[m * M + c];
-                if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1) ? m * M + c : 0];
+                if (HOLD == 4) cr[c] = vside[(M * M + m * M + c) * side_stride];
+                else if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
-                if (HOLD >= 2) ci[c] = Ci[(HOLD >= 2) ? m * M + c : 0];
+                if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
+                else if (HOLD >= 3) ci[c] = vside[(m * M + c) * side_stride];
                 else ci[c] = -dmul(zi_s, q);
             }
             zgemv_rowdot<M, V>(cr, ci, ur, ui, yr, yi);
@@ -554,7 +564,17 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
 
 template <int M, int KIND, int V, bool DENSE, int HOLD, int MINB = 1, int BLOCK = kBlock>
 __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepParams<M> p) {
-    step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x);
+    if constexpr (HOLD >= 3) {
+        extern __shared__ double side_smem[];  // [M*M or 2*M*M][BLOCK]: Im(C) (and Re(C)) of every thread, conflict free
+        step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x, side_smem + threadIdx.x, BLOCK);
+    } else {
+        step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x);
+    }
+}
+
+template <int M, int HOLD, int BLOCK = kBlock>
+constexpr size_t step_kernel_smem_bytes() {
+    return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double) : (HOLD == 4 ? (size_t)2 * M * M * BLOCK * sizeof(double) : 0);
 }
 #endif
 

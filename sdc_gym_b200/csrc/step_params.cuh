@@ -66,17 +66,21 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
     p.old_states = io->old_states;
 }
 
-// Register-residency policy for C and occupancy target (measured on B200, profiles/tuning_r01.md):
-// diag kernels keep Re(C) in registers and re-derive Im(C) = -zi*q from the constant bank (166 registers,
-// 3 blocks of 128 threads per SM) up to M=5, Re only up to M=7, nothing beyond; dense kernels spend their
-// registers on the M x M inverse instead.
+// Where the system matrix C lives and how many blocks share an SM (measured on B200, profiles/README.md):
+//  * full-solve diag kernels, M >= 5: all of C in shared memory (HOLD 4; [2 M^2][block] doubles, conflict free).
+//    The sweep is bound by dependent-issue latency, not FP64 throughput, so what pays is warps per SM: with C out
+//    of the register file the M=5 kernel fits 16 warps/SM (8 % faster than Re(C) in registers at 12 warps/SM).
+//    M = 7 / 9 do not fit C in registers at all (255 + spills before).
+//  * M <= 4: C is small enough to stay in registers.
+//  * dense kernels spend their registers on the M x M inverse; sdc-v1 runs one sweep per launch and is memory
+//    bound: nothing is held, occupancy is maximised.
 template <int M>
 struct HoldPolicy {
-    static constexpr int diag = (M <= 7) ? 1 : 0;
-    static constexpr int diag_minb = (M <= 5) ? 3 : 2;
+    static constexpr int diag = (M <= 4) ? 1 : ((M <= 7) ? 4 : 0);  // M >= 8: 2 blocks of 64 threads lose to recomputing
+    static constexpr int diag_minb = (M <= 5) ? 4 : 2;
+    static constexpr int diag_block = 128;
     static constexpr int dense = (M <= 3) ? 2 : 0;
     static constexpr int dense_minb = 2;
-    // sdc-v1 runs a single sweep per launch and is memory bound: nothing is worth holding, occupancy is
     static constexpr int step = 0;
     static constexpr int step_minb = (M <= 5) ? 4 : 2;
 };
