@@ -75,6 +75,26 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         }
     }
 #endif
+#ifdef SDCGYM_TUNE_VARIANTS
+    if constexpr (kM == 5 && KIND == SDCGYM_ENV_STEP && !DENSE && V == 0) {
+        switch (tune_variant()) {
+#define SDCGYM_TV1(n, MINB, BLK)                                                                        \
+        case n: step_kernel<kM, KIND, V, DENSE, 0, MINB, BLK><<<(unsigned)((p.N + BLK - 1) / BLK), BLK, 0, s>>>(p); \
+            return cudaGetLastError();
+        SDCGYM_TV1(1, 2, 128)
+        SDCGYM_TV1(2, 3, 128)
+        SDCGYM_TV1(3, 4, 128)
+        SDCGYM_TV1(4, 5, 128)
+        SDCGYM_TV1(5, 6, 128)
+        SDCGYM_TV1(6, 8, 128)
+        SDCGYM_TV1(7, 4, 256)
+        SDCGYM_TV1(8, 12, 64)
+        SDCGYM_TV1(9, 16, 64)
+#undef SDCGYM_TV1
+        default: break;
+        }
+    }
+#endif
     constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
     constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);

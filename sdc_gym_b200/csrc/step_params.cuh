@@ -82,7 +82,7 @@ struct HoldPolicy {
     static constexpr int dense = (M <= 3) ? 2 : 0;
     static constexpr int dense_minb = 2;
     static constexpr int step = 0;
-    static constexpr int step_minb = (M <= 5) ? 4 : 2;
+    static constexpr int step_minb = (M <= 5) ? 6 : ((M <= 7) ? 3 : 2);  // M=5: 80 regs, 24 warps/SM: +12 % (profiles/tune_r01_v1.log)
 };
 
 }  // namespace sdcgym
