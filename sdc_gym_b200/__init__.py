@@ -20,7 +20,7 @@ REGISTRY = {
     "sdc-v1": ("SDC_Step_Env", 50),
 }
 
-__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize",
+__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan",
            "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY"]
 
 
@@ -32,9 +32,9 @@ def __getattr__(name):
     if name in ("SpectralRadiusLoss", "ResidualLoss"):
         from . import loss
         return getattr(loss, name)
-    if name == "VecNormalize":
-        from .vec_normalize import VecNormalize
-        return VecNormalize
+    if name in ("VecNormalize", "VecCheckNan"):
+        from . import vec_normalize
+        return getattr(vec_normalize, name)
     raise AttributeError(name)
 
 
@@ -67,4 +67,7 @@ def make_env(args, num_envs=None, include_norm=False, norm_reward=True, **kwargs
         model_kwargs = getattr(args, "model_kwargs", None) or {}
         extra = {"gamma": model_kwargs["gamma"]} if "gamma" in model_kwargs else {}
         env = VecNormalize(env, norm_obs=getattr(args, "norm_obs", True), norm_reward=norm_reward, **extra)
+    if getattr(args, "debug_nans", False):
+        from .vec_normalize import VecCheckNan
+        env = VecCheckNan(env, raise_exception=True)
     return env

@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-fmad=false",  # never contract a*b+c: every FMA in the kernels is an explicit __fma_rn
     "-Xcompiler", "-fPIC",
 ]
+NVCC_FLAGS += os.environ.get("SDCGYM_EXTRA_NVCC_FLAGS", "").split()  # experiments only
 if os.environ.get("SDCGYM_TUNE_VARIANTS") == "1":  # experiment builds only: extra (occupancy, residency) variants
     NVCC_FLAGS.append("-DSDCGYM_TUNE_VARIANTS")
 

@@ -74,13 +74,16 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
 //  * M <= 4: C is small enough to stay in registers.
 //  * dense kernels spend their registers on the M x M inverse; sdc-v1 runs one sweep per launch and is memory
 //    bound: nothing is held, occupancy is maximised.
+#ifndef SDCGYM_DENSE_MINB
+#define SDCGYM_DENSE_MINB 3
+#endif
 template <int M>
 struct HoldPolicy {
     static constexpr int diag = (M <= 4) ? 1 : ((M <= 7) ? 4 : 0);  // M >= 8: 2 blocks of 64 threads lose to recomputing
     static constexpr int diag_minb = (M <= 5) ? 4 : 2;
     static constexpr int diag_block = 128;
-    static constexpr int dense = (M <= 3) ? 2 : 0;
-    static constexpr int dense_minb = 2;
+    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : 0);
+    static constexpr int dense_minb = (M == 4 || M == 5) ? SDCGYM_DENSE_MINB : 2;
     static constexpr int step = 0;
     static constexpr int step_minb = (M <= 5) ? 6 : ((M <= 7) ? 3 : 2);  // M=5: 80 regs, 24 warps/SM: +12 % (profiles/tune_r01_v1.log)
 };

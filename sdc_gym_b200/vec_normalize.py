@@ -236,3 +236,51 @@ class VecNormalize:
 
     def close(self):
         self.venv.close()
+
+
+class VecCheckNan:
+    """``VecCheckNan(env, raise_exception=True)`` as used by the reference under ``--debug_nans``
+    (``utils/utils.py:313-314``): raises ``ValueError`` when an action, observation or reward is NaN / Inf."""
+
+    def __init__(self, venv, raise_exception=True, warn_once=True, check_inf=True):
+        self.venv, self.raise_exception, self.check_inf = venv, raise_exception, check_inf
+
+    def __getattr__(self, name):
+        return getattr(self.venv, name)
+
+    def _check(self, **arrays):
+        for name, x in arrays.items():
+            if x is None:
+                continue
+            if hasattr(x, "is_cuda"):
+                t = _torch().view_as_real(x) if x.is_complex() else x
+                bad = bool((t.isnan() | (t.isinf() if self.check_inf else False)).any())
+            else:
+                a = np.asarray(x)
+                if a.dtype == object:
+                    continue
+                bad = bool(np.isnan(a).any() or (self.check_inf and np.isinf(a).any()))
+            if bad:
+                msg = f"found nan or inf in {name}"
+                if self.raise_exception:
+                    raise ValueError(msg)
+                import warnings
+                warnings.warn(msg)
+
+    def reset(self, **kw):
+        obs = self.venv.reset(**kw)
+        self._check(observations=obs)
+        return obs
+
+    def step(self, actions):
+        if self.venv.prec is None:
+            self._check(actions=actions)
+        obs, rew, done, infos = self.venv.step(actions)
+        self._check(observations=obs, rewards=rew)
+        return obs, rew, done, infos
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)

@@ -117,3 +117,28 @@ def test_residual_loss_against_numpy(prec_type):
         assert np.all(np.abs(r_new.cpu().numpy() - ref_r) <= 1e-11 * scale)
         ref_loss = np.abs(ref_r).max(axis=1).mean()
         assert abs(float(val) - ref_loss) <= 1e-10 * ref_loss
+
+
+def test_make_env_mirrors_reference_factory_and_check_nan():
+    import types
+    args = types.SimpleNamespace(envname="sdc-v1", num_envs=64, M=3, dt=1.0, restol=1e-10, seed=5,
+                                 lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0],
+                                 lambda_real_interpolation_interval=None, norm_factor=1, residual_weight=0.5,
+                                 step_penalty=0.1, reward_iteration_only=True, reward_strategy="iteration_only",
+                                 collect_states=False, model_class="PPG", model_kwargs={"gamma": 0.9}, norm_obs=True,
+                                 debug_nans=True)
+    env = sdc_gym_b200.make_env(args, include_norm=True)
+    assert isinstance(env, sdc_gym_b200.VecCheckNan) and env.num_envs == 64 and env.venv.gamma == 0.9
+    obs = env.reset()
+    assert obs.shape == (64, 2, 3)
+    obs, rew, done, infos = env.step(np.zeros((64, 3)))
+    assert np.all(rew <= 10) and len(infos) == 64
+    with pytest.raises(ValueError):
+        env.step(np.full((64, 3), np.nan))
+    # kwargs beat args, fixed preconditioner ignores (uninitialised) actions
+    env2 = sdc_gym_b200.make_env(args, num_envs=8, prec="LU", M=5)
+    assert env2.num_envs == 8 and env2.envs[0].prec == "LU" and env2.envs[0].M == 5
+    env2.reset()
+    action = [np.empty(env2.action_space.shape, dtype=env2.action_space.dtype) for _ in range(8)]
+    o, r, d, i = env2.step(action)
+    assert o.shape == (8, 2, 5)
