@@ -200,6 +200,15 @@ int sdcgym_vecnorm_returns(int64_t N, const double* reward, double gamma, double
 int sdcgym_vecnorm_reward(int64_t N, const double* reward, const uint8_t* flags, const double* ret_var, double eps,
                           double clip, int normalize, double* out, double* returns, void* stream);
 
+/*
+ * Generalised advantage estimation over a device rollout of T steps x N envs (arrays [T][N], env index fastest):
+ * SB3 RolloutBuffer.compute_returns_and_advantage, the consumer of the rollouts rl_playground.py collects through
+ * model.learn (rl_playground.py:286).  episode_starts[t][i] != 0 marks that step t begins a new episode of env i.
+ */
+int sdcgym_gae(int T, int64_t N, const double* rewards, const double* values, const uint8_t* episode_starts,
+               const double* last_values, const uint8_t* last_dones, double gamma, double gae_lambda,
+               double* advantages, double* returns, void* stream);
+
 /* sum of x[0..N) in fp64 with a fixed (N-independent per block, deterministic) reduction tree -> out[0] */
 int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream);
 

@@ -20,7 +20,7 @@ REGISTRY = {
     "sdc-v1": ("SDC_Step_Env", 50),
 }
 
-__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan",
+__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts",
            "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY"]
 
 
@@ -35,6 +35,9 @@ def __getattr__(name):
     if name in ("VecNormalize", "VecCheckNan"):
         from . import vec_normalize
         return getattr(vec_normalize, name)
+    if name in ("RolloutBuffer", "collect_rollouts"):
+        from . import rollout
+        return getattr(rollout, name)
     raise AttributeError(name)
 
 

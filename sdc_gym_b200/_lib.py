@@ -158,6 +158,8 @@ def load():
     L.sdcgym_vecnorm_apply.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, dbl, dbl, vp, vp]
     L.sdcgym_vecnorm_returns.argtypes = [i64, vp, dbl, vp, vp]
     L.sdcgym_vecnorm_reward.argtypes = [i64, vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
+    L.sdcgym_gae.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
+    L.sdcgym_gae.restype = ctypes.c_int
     for name in ("sdcgym_residual_step", "sdcgym_vecnorm_scratch_doubles", "sdcgym_vecnorm_accumulate",
                  "sdcgym_vecnorm_merge", "sdcgym_vecnorm_apply", "sdcgym_vecnorm_returns", "sdcgym_vecnorm_reward"):
         getattr(L, name).restype = ctypes.c_int

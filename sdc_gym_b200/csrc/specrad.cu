@@ -3,8 +3,11 @@
 
 namespace sdcgym {
 
+#ifndef SDCGYM_RHO_MINB
+#define SDCGYM_RHO_MINB 4  // 128 registers, 16 warps/SM: +25 % over 2 blocks/SM (profiles/README.md)
+#endif
 template <int M>
-__global__ void __launch_bounds__(128) rho_kernel(const __grid_constant__ RhoParams<M> p) {
+__global__ void __launch_bounds__(128, (M <= 5) ? SDCGYM_RHO_MINB : 1) rho_kernel(const __grid_constant__ RhoParams<M> p) {
     rho_one<M>(p, (int64_t)blockIdx.x * 128 + threadIdx.x);
 }
 

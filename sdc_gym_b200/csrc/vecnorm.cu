@@ -206,9 +206,46 @@ static int launch_residual(const sdcgym_rho_desc* d, int64_t N, const double* la
     return (int)cudaGetLastError();
 }
 
+// ---- generalised advantage estimation over a device rollout (SB3 RolloutBuffer.compute_returns_and_advantage) ----
+// one thread per env, reverse scan over the T stored steps; every access is coalesced along the env axis.
+__global__ void __launch_bounds__(256) gae_kernel(int T, int64_t N, const double* __restrict__ rewards,
+                                                  const double* __restrict__ values,
+                                                  const uint8_t* __restrict__ episode_starts,
+                                                  const double* __restrict__ last_values,
+                                                  const uint8_t* __restrict__ last_dones, double gamma, double lam,
+                                                  double* __restrict__ advantages, double* __restrict__ returns) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    double last_gae = 0.0;
+    double next_value = last_values[i];
+    double next_non_terminal = last_dones[i] ? 0.0 : 1.0;
+    for (int t = T - 1; t >= 0; t--) {
+        const int64_t k = (int64_t)t * N + i;
+        const double v = values[k];
+        const double delta = rewards[k] + gamma * next_value * next_non_terminal - v;
+        last_gae = delta + gamma * lam * next_non_terminal * last_gae;
+        advantages[k] = last_gae;
+        returns[k] = last_gae + v;
+        next_value = v;
+        next_non_terminal = episode_starts[k] ? 0.0 : 1.0;
+    }
+}
+
 }  // namespace sdcgym
 
 using namespace sdcgym;
+
+extern "C" int sdcgym_gae(int T, int64_t N, const double* rewards, const double* values, const uint8_t* episode_starts,
+                          const double* last_values, const uint8_t* last_dones, double gamma, double gae_lambda,
+                          double* advantages, double* returns, void* stream) {
+    if (T < 0 || N < 0) return SDCGYM_EINVAL;
+    if (T == 0 || N == 0) return 0;
+    if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns) return SDCGYM_ENULL;
+    gae_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, N, rewards, values, episode_starts,
+                                                                            last_values, last_dones, gamma, gae_lambda,
+                                                                            advantages, returns);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2; }
 

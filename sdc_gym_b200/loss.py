@@ -57,7 +57,7 @@ class SpectralRadiusLoss:
         torch = _torch()
         if self.prec is not None:
             return None, 0, 0
-        t = outputs if isinstance(outputs, torch.Tensor) else torch.as_tensor(np.asarray(outputs))
+        t = outputs if isinstance(outputs, torch.Tensor) else torch.as_tensor(np.array(outputs))
         t = t.to(self.device)
         is_c = t.is_complex()
         t = t.to(torch.complex128 if is_c else torch.float64)

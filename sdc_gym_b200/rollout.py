@@ -1,0 +1,123 @@
+"""Device-resident rollout collection for the RL caller of the path (``rl_playground.py:286`` ``model.learn`` ->
+SB3 ``collect_rollouts``; BASELINE config "PPG rollout collection, sdc-v1, norm_obs").
+
+``RolloutBuffer`` keeps observations (as planes), actions, rewards, episode starts, values and log-probs of
+``n_steps`` x ``num_envs`` transitions in HBM and computes returns / GAE advantages with one kernel
+(``sdcgym_gae``, SB3 semantics).  ``collect_rollouts`` drives a (normalised) ``SDCVecEnv`` with a policy callable
+without any host round trip per step.  The learner itself (PPO/PPG update) is out of scope.
+"""
+from __future__ import annotations
+
+import ctypes
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class RolloutBuffer:
+    def __init__(self, n_steps, num_envs, obs_planes, action_dim, device, gamma=0.99, gae_lambda=0.95,
+                 obs_dtype=None, action_is_complex=False):
+        torch = _torch()
+        self.n_steps, self.num_envs, self.P, self.A = int(n_steps), int(num_envs), int(obs_planes), int(action_dim)
+        self.gamma, self.gae_lambda = float(gamma), float(gae_lambda)
+        self.device = torch.device(device)
+        f64 = torch.float64
+        T, N = self.n_steps, self.num_envs
+        self.observations = torch.zeros((T, self.P, N), dtype=obs_dtype or f64, device=self.device)
+        self.actions = torch.zeros((T, N, self.A), dtype=torch.complex128 if action_is_complex else f64,
+                                   device=self.device)
+        self.rewards = torch.zeros((T, N), dtype=f64, device=self.device)
+        self.values = torch.zeros((T, N), dtype=f64, device=self.device)
+        self.log_probs = torch.zeros((T, N), dtype=f64, device=self.device)
+        self.episode_starts = torch.zeros((T, N), dtype=torch.uint8, device=self.device)
+        self.advantages = torch.zeros((T, N), dtype=f64, device=self.device)
+        self.returns = torch.zeros((T, N), dtype=f64, device=self.device)
+        self.pos = 0
+        self.full = False
+        self._L = _lib.load()
+
+    def reset(self):
+        self.pos, self.full = 0, False
+
+    def add(self, obs_planes, actions, rewards, episode_starts, values=None, log_probs=None):
+        """Store one transition of every env.  ``obs_planes``: (P, N) tensor (the observation the action was taken
+        on), ``episode_starts``: uint8/bool (N,)."""
+        if self.pos >= self.n_steps:
+            raise IndexError("rollout buffer is full")
+        t = self.pos
+        self.observations[t].copy_(obs_planes)
+        self.actions[t].copy_(actions)
+        self.rewards[t].copy_(rewards)
+        self.episode_starts[t].copy_(episode_starts)
+        if values is not None:
+            self.values[t].copy_(values)
+        if log_probs is not None:
+            self.log_probs[t].copy_(log_probs)
+        self.pos += 1
+        self.full = self.pos == self.n_steps
+
+    def compute_returns_and_advantage(self, last_values, dones):
+        """SB3 ``RolloutBuffer.compute_returns_and_advantage(last_values, dones)`` on the device."""
+        torch = _torch()
+        lv = last_values.to(self.device, torch.float64).contiguous()
+        ld = dones.to(self.device).to(torch.uint8).contiguous()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self._L.sdcgym_gae(self.pos, self.num_envs, self.rewards.data_ptr(), self.values.data_ptr(),
+                                      self.episode_starts.data_ptr(), lv.data_ptr(), ld.data_ptr(), self.gamma,
+                                      self.gae_lambda, self.advantages.data_ptr(), self.returns.data_ptr(), stream),
+                   "sdcgym_gae")
+        self._keep = (lv, ld)
+        return self.advantages[: self.pos], self.returns[: self.pos]
+
+
+def collect_rollouts(env, policy, n_steps, buffer=None, gamma=0.99, gae_lambda=0.95):
+    """Collect ``n_steps`` transitions of every env on the device.
+
+    ``env``: ``VecNormalize`` (or bare ``SDCVecEnv``) that has been ``reset()``.
+    ``policy(obs_planes) -> (actions, values, log_probs)`` with ``obs_planes`` a (4M, N) CUDA tensor; ``values`` /
+    ``log_probs`` may be ``None``.  Returns the filled ``RolloutBuffer`` (returns and advantages computed with the
+    policy's value of the final observation)."""
+    torch = _torch()
+    venv = getattr(env, "venv", env)
+    N, M = venv.num_envs, venv.M
+    normalised = env is not venv and getattr(env, "norm_obs", False)
+
+    def current_obs():
+        return env.norm_planes[:, :N] if normalised else venv.S[:, :N]
+
+    if buffer is None:
+        buffer = RolloutBuffer(n_steps, N, 4 * M, venv._kernel_n_act or venv.n_act, venv.device, gamma, gae_lambda,
+                               action_is_complex=venv.free_action_space)
+    buffer.reset()
+    starts = getattr(env, "_last_episode_starts", None)
+    if starts is None:
+        starts = torch.ones(N, dtype=torch.uint8, device=venv.device)
+    dones = starts
+    for _ in range(n_steps):
+        obs = current_obs()
+        actions, values, log_probs = policy(obs)
+        buffer.observations[buffer.pos].copy_(obs)  # before the step overwrites the planes
+        out = env.step_tensor(actions if venv._kernel_n_act else None)
+        dones = (out["flags"] & _lib.FLAG_DONE).ne(0)
+        t = buffer.pos
+        buffer.actions[t].copy_(actions)
+        buffer.rewards[t].copy_(out["reward"])
+        buffer.episode_starts[t].copy_(starts)
+        if values is not None:
+            buffer.values[t].copy_(values)
+        if log_probs is not None:
+            buffer.log_probs[t].copy_(log_probs)
+        buffer.pos += 1
+        starts = dones.to(torch.uint8)
+    buffer.full = buffer.pos == buffer.n_steps
+    env._last_episode_starts = starts
+    _, last_values, _ = policy(current_obs())
+    if last_values is None:
+        last_values = torch.zeros(N, dtype=torch.float64, device=venv.device)
+    buffer.compute_returns_and_advantage(last_values, dones)
+    return buffer

@@ -142,3 +142,46 @@ def test_make_env_mirrors_reference_factory_and_check_nan():
     action = [np.empty(env2.action_space.shape, dtype=env2.action_space.dtype) for _ in range(8)]
     o, r, d, i = env2.step(action)
     assert o.shape == (8, 2, 5)
+
+
+def test_gae_kernel_and_rollout_collection():
+    import torch
+    from sdc_gym_b200.rollout import RolloutBuffer, collect_rollouts
+    T, N = 17, 1000
+    rng = np.random.default_rng(3)
+    rew, val = rng.normal(size=(T, N)), rng.normal(size=(T, N))
+    starts = rng.random((T, N)) < 0.1
+    last_v, last_d = rng.normal(size=N), rng.random(N) < 0.2
+    buf = RolloutBuffer(T, N, 4, 2, "cuda", gamma=0.97, gae_lambda=0.9)
+    for t in range(T):
+        buf.add(torch.zeros(4, N, device="cuda"), torch.zeros(N, 2, device="cuda"), torch.as_tensor(rew[t]).cuda(),
+                torch.as_tensor(starts[t]).cuda(), torch.as_tensor(val[t]).cuda())
+    adv, ret = buf.compute_returns_and_advantage(torch.as_tensor(last_v), torch.as_tensor(last_d))
+    # stable_baselines3.common.buffers.RolloutBuffer.compute_returns_and_advantage, restated
+    ref = np.zeros((T, N)); last = 0
+    for t in reversed(range(T)):
+        nnt = 1.0 - (last_d if t == T - 1 else starts[t + 1]).astype(float)
+        nv = last_v if t == T - 1 else val[t + 1]
+        delta = rew[t] + 0.97 * nv * nnt - val[t]
+        last = delta + 0.97 * 0.9 * nnt * last
+        ref[t] = last
+    assert np.allclose(adv.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    assert np.allclose(ret.cpu().numpy(), ref + val, rtol=1e-12, atol=1e-12)
+    # rollout collection with a device policy over the normalised sdc-v1 env
+    n = 2048
+    env = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=1, output="torch", **KW))
+    env.reset()
+    x = torch.as_tensor(np.diag(fixed_preconditioner("min", 5)), device="cuda")
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+
+    def policy(obs_planes):
+        a = 2 * (x[None] + (torch.rand((n, 5), dtype=torch.float64, device="cuda", generator=gen) - 0.5) * 0.2) - 1
+        return a, obs_planes[0] * 0.1, None
+
+    b = collect_rollouts(env, policy, 24)
+    assert b.full and b.observations.shape == (24, 20, n)
+    assert bool(b.episode_starts[0].all()) and int(b.episode_starts[1:].sum()) > 0
+    assert torch.isfinite(b.advantages).all() and torch.isfinite(b.returns).all()
+    assert torch.allclose(b.values, b.observations[:, 0] * 0.1)
+    b2 = collect_rollouts(env, policy, 24, buffer=b)  # continues the episodes
+    assert b2 is b and not bool(b.episode_starts[0].all())

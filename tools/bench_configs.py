@@ -100,7 +100,25 @@ for M in (5,):
     print(json.dumps({"config": "sdc-v1 rollout + device VecNormalize(norm_obs, norm_reward)", "M": M, "envs": N,
                       "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
                       "time_for_64M_env_steps_s": (1 << 26) / (N / ms * 1e3)}), flush=True)
-    del env, vn
+    # full rollout collection: random policy, observations/actions/rewards stored in a device RolloutBuffer, GAE
+    from sdc_gym_b200.rollout import RolloutBuffer, collect_rollouts
+    Nr, T = 1 << 20, 16
+    env_r = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=Nr, M=M, reward_iteration_only=False, **KW))
+    env_r.reset()
+    def policy(obs_planes):
+        a = torch.rand((Nr, M), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        return a, obs_planes[0], None
+    buf = collect_rollouts(env_r, policy, T)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        buf = collect_rollouts(env_r, policy, T, buffer=buf)
+    torch.cuda.synchronize()
+    el = (time.perf_counter() - t0) / 4
+    print(json.dumps({"config": "sdc-v1 rollout collection (VecNormalize + RolloutBuffer + GAE, random policy)", "M": M,
+                      "envs": Nr, "n_steps": T, "s_per_rollout": el, "env_steps_per_s": Nr * T / el,
+                      "time_for_64M_env_steps_s": (1 << 26) / (Nr * T / el)}), flush=True)
+    del env, vn, env_r, buf
     torch.cuda.empty_cache()
 # ---- config 3: spectral radius grid ----
 from sdc_gym_b200.loss import SpectralRadiusLoss
