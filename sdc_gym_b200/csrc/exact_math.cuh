@@ -279,10 +279,11 @@ SDCGYM_HD double inf_norm_fast(const double (&vr)[M], const double (&vi)[M]) {
 // ---------------------------------------------------------------------------------------------------
 template <int M, int V>
 SDCGYM_HD_NOINLINE void cinv_exact(cplx* __restrict__ A /*M*M col-major, in: P, out: LU*/,
-                                        cplx* __restrict__ B /*M*M col-major, out: inverse*/) {
+                                        cplx* __restrict__ B /*M*M col-major, out: inverse*/,
+                                        const int stride = 1 /*distance between consecutive elements, in cplx*/) {
     int ipiv[M];
     cplx b[M];
-#define AT_(X, i, j) X[(i) + (j) * M]
+#define AT_(X, i, j) X[((i) + (j) * M) * stride]
 #pragma unroll 1
     for (int j = 0; j < M; j++) {
         for (int i = 0; i < M; i++) b[i] = AT_(A, i, j);
@@ -371,7 +372,7 @@ SDCGYM_HD_NOINLINE void cinv_exact(cplx* __restrict__ A /*M*M col-major, in: P, 
     }
 
     // B = I with the row swaps applied
-    for (int i = 0; i < M * M; i++) B[i] = cplx{0.0, 0.0};
+    for (int i = 0; i < M * M; i++) B[i * stride] = cplx{0.0, 0.0};
     for (int i = 0; i < M; i++) AT_(B, i, i).re = 1.0;
     for (int i = 0; i < M; i++) {
         int p = ipiv[i];

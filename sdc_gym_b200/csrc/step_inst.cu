@@ -98,7 +98,7 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
     constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);
-    constexpr int block = (!DENSE && !kStep) ? HoldPolicy<kM>::diag_block : kBlock;
+    constexpr int block = DENSE ? HoldPolicy<kM>::dense_block : ((!kStep) ? HoldPolicy<kM>::diag_block : kBlock);
     static_assert(!(DENSE && kStep && hold >= 3) || true, "");
     constexpr size_t smem = step_kernel_smem_bytes<kM, hold, block>();
     auto kernel = step_kernel<kM, KIND, V, DENSE, hold, minb, block>;

@@ -248,7 +248,9 @@ SDCGYM_HD HiBand make_band(double t) {
 // the exact np.linalg.inv emulation (any non-diagonal Q_delta), otherwise Pinv is diagonal (prec=None,
 // diag actions).  HOLD: 2 = keep Re and Im of C in registers, 1 = only Re (Im re-derived from the constant bank),
 // 0 = recompute z*q on use, 3 = Re in registers and Im in shared memory (`side`, element k of this thread at
-// side[k * side_stride]; the LDS run on the memory pipe beside the saturated FP64 pipe).
+// side[k * side_stride]; the LDS run on the memory pipe beside the saturated FP64 pipe), 4 = Re and Im in shared
+// memory, 5 (dense kernels with M > kRegInvMaxM) = C *and* the M x M inverse in shared memory as complex pairs
+// (`pside`: elements [0, M^2) hold the LU work matrix during the inverse and C afterwards, [M^2, 2 M^2) hold Pinv).
 // =====================================================================================================
 #ifdef __CUDA_ARCH__
 #define SDCGYM_WARP_ANY(x) __any_sync(0xffffffffu, (x))
@@ -257,7 +259,8 @@ SDCGYM_HD HiBand make_band(double t) {
 #endif
 
 template <int M, int KIND, int V, bool DENSE, int HOLD>
-SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1) {
+SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1,
+                        cplx* pside = nullptr, const int pstride = 1) {
     const bool valid = tid < p.N;
     const int64_t i = valid ? tid : p.N - 1;
     const int64_t ld = p.ld;
@@ -266,7 +269,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     const double zr = dmul(lr, p.dt), zi = dmul(li, p.dt);
 
     // ---- preconditioner inverse ----
-    constexpr int NP = DENSE ? M * M : M;
+    constexpr bool PS = DENSE && (HOLD == 5);  // Pinv (and C) live in the complex side store
+    static_assert(HOLD != 5 || (DENSE && M > kRegInvMaxM), "HOLD 5 is for the large dense kernels");
+    constexpr int NP = DENSE ? (PS ? 1 : M * M) : M;
     double Pr[NP], Pi[NP];
     if (!DENSE) {
 #pragma unroll
@@ -336,6 +341,17 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                     Pr[DENSE ? r * M + c : 0] = Br[r + c * M];
                     Pi[DENSE ? r * M + c : 0] = Bi[r + c * M];
                 }
+        } else if constexpr (PS) {
+            cplx* A = pside;                                // LU work matrix now, C later (same per-thread slots)
+            cplx* B = pside + (size_t)M * M * pstride;      // the inverse stays here
+#pragma unroll 1
+            for (int r = 0; r < M; r++)
+#pragma unroll 1
+                for (int c = 0; c < M; c++) {
+                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    A[(r + c * M) * pstride] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
+                }
+            cinv_exact<M, V>(A, B, pstride);
         } else {
             cplx A[M * M], B[M * M];  // column-major work arrays (local memory)
 #pragma unroll 1
@@ -369,7 +385,8 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 if (HOLD <= 3) Cr[(HOLD >= 1 && HOLD <= 3) ? r * M + c : 0] = crv;
                 if (HOLD == 4) side[(M * M + r * M + c) * side_stride] = crv;
                 if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
-                if (HOLD >= 3) side[(r * M + c) * side_stride] = -dmul(zi, q);
+                if (HOLD == 3 || HOLD == 4) side[(r * M + c) * side_stride] = -dmul(zi, q);
+                if (HOLD == 5) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
             }
     }
 
@@ -398,7 +415,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         double zr_s = zr, zi_s = zi;
         // volatile: the side store is loop invariant, and a hoisted load is a register again
         const volatile double* vside = side;
+        const volatile cplx* vp = pside;
         (void)vside;
+        (void)vp;
 #ifdef __CUDA_ARCH__
         if (HOLD < 2) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
 #endif
@@ -411,8 +430,13 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 double ar[M], ai[M];
 #pragma unroll
                 for (int c = 0; c < M; c++) {
-                    ar[c] = Pr[DENSE ? m * M + c : 0];
-                    ai[c] = Pi[DENSE ? m * M + c : 0];
+                    if (PS) {
+                        ar[c] = vp[(M * M + m + c * M) * pstride].re;  // B is column-major
+                        ai[c] = vp[(M * M + m + c * M) * pstride].im;
+                    } else {
+                        ar[c] = Pr[(DENSE && !PS) ? m * M + c : 0];
+                        ai[c] = Pi[(DENSE && !PS) ? m * M + c : 0];
+                    }
                 }
                 zgemv_rowdot<M, V>(ar, ai, rr, ri, dr[m], di[m]);
             }
@@ -428,10 +452,12 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
 #pragma unroll
             for (int c = 0; c < M; c++) {
                 double q = p.Q[m * M + c];
-                if (HOLD == 4) cr[c] = vside[(M * M + m * M + c) * side_stride];
+                if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
+                else if (HOLD == 4) cr[c] = vside[(M * M + m * M + c) * side_stride];
                 else if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
-                if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
+                if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
+                else if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
                 else if (HOLD >= 3) ci[c] = vside[(m * M + c) * side_stride];
                 else ci[c] = -dmul(zi_s, q);
             }
@@ -564,7 +590,11 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
 
 template <int M, int KIND, int V, bool DENSE, int HOLD, int MINB = 1, int BLOCK = kBlock>
 __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepParams<M> p) {
-    if constexpr (HOLD >= 3) {
+    if constexpr (HOLD == 5) {
+        extern __shared__ double2 pside_smem[];  // [2*M*M][BLOCK] complex: LU/C then Pinv of every thread
+        step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x, nullptr, 1,
+                                          reinterpret_cast<cplx*>(pside_smem) + threadIdx.x, BLOCK);
+    } else if constexpr (HOLD >= 3) {
         extern __shared__ double side_smem[];  // [M*M or 2*M*M][BLOCK]: Im(C) (and Re(C)) of every thread, conflict free
         step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x, side_smem + threadIdx.x, BLOCK);
     } else {
@@ -574,7 +604,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
 
 template <int M, int HOLD, int BLOCK = kBlock>
 constexpr size_t step_kernel_smem_bytes() {
-    return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double) : (HOLD == 4 ? (size_t)2 * M * M * BLOCK * sizeof(double) : 0);
+    return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double)
+                     : (HOLD == 4 ? (size_t)2 * M * M * BLOCK * sizeof(double)
+                                  : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double) : 0));
 }
 #endif
 
