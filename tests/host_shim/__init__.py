@@ -43,6 +43,7 @@ def shim():
         vp = ctypes.c_void_p
         L.shim_reset.argtypes = [ctypes.POINTER(_lib.EnvDesc), ctypes.POINTER(_lib.State), vp, vp, vp]
         L.shim_step.argtypes = [ctypes.POINTER(_lib.EnvDesc), ctypes.POINTER(_lib.State), ctypes.POINTER(_lib.StepIO)]
+        L.shim_step_hold5.argtypes = L.shim_step.argtypes
         L.shim_spectral_radius.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64, vp, vp, vp]
         _shim = L
     return _shim
@@ -75,8 +76,9 @@ def make_desc(kind, M, *, prec=None, prec_type="diag", dt=1.0, restol=1e-10, cpl
 class ShimBatch:
     """Planar state of n envs in host memory, stepped by the host-compiled kernel bodies."""
 
-    def __init__(self, desc, n, collect=False):
+    def __init__(self, desc, n, collect=False, entry="shim_step"):
         self.d, self.n, self.M = desc, n, desc.M
+        self.entry = entry
         self.ld = max(32, (n + 31) // 32 * 32)
         M, ld = self.M, self.ld
         self.lam = np.zeros((2, ld))
@@ -135,7 +137,7 @@ class ShimBatch:
         io.info_residual, io.info_niter = self.info_res.ctypes.data, self.info_niter.ctypes.data
         io.info_lam, io.terminal_obs = self.info_lam.ctypes.data, self.term.ctypes.data
         io.old_states = None if self.old_states is None else self.old_states.ctypes.data
-        rc = shim().shim_step(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
+        rc = getattr(shim(), self.entry)(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
         assert rc == 0
         n = self.n
         f = self.flags[:n]

@@ -105,6 +105,32 @@ extern "C" int shim_step(const sdcgym_env_desc* d, const sdcgym_state* st, const
     return -2;
 }
 
+// ---- the shared-memory formulation of the large dense kernels (HOLD 5), not selected by HoldPolicy but kept
+//      parity-tested ----
+template <int M>
+static int step_m_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    if constexpr (M > kRegInvMaxM) {
+        StepParams<M> p;
+        fill_params<M>(p, d, st);
+        fill_step_io<M>(p, io);
+        cplx pside[3 * 2 * M * M];  // stride 3
+        for (int64_t i = 0; i < p.N; i++) {
+            if (d->env_kind == SDCGYM_ENV_FULL) step_one<M, 0, 0, true, 5>(p, i, nullptr, 1, pside, 3);
+            else step_one<M, 1, 0, true, 5>(p, i, nullptr, 1, pside, 3);
+        }
+        return 0;
+    }
+    return -2;
+}
+extern "C" int shim_step_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    switch (d->M) {
+    case 6: return step_m_hold5<6>(d, st, io);
+    case 7: return step_m_hold5<7>(d, st, io);
+    case 9: return step_m_hold5<9>(d, st, io);
+    }
+    return -2;
+}
+
 // ---- spectral radius ----
 #include "../../sdc_gym_b200/csrc/specrad_params.cuh"
 

@@ -11,13 +11,13 @@ from tests.helpers import assert_reward_close, assert_same
 
 
 def _run(kind, M, n, *, prec=None, prec_type="diag", mode="good", steps=1, strategy="iteration_only", seed=0,
-         im_int=(-10, 0), variant=0):
+         im_int=(-10, 0), variant=0, entry="shim_step"):
     rng = np.random.default_rng(seed)
     Q = collocation_matrix(M)
     lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(im_int[0], im_int[1], n)
     d = host_shim.make_desc(kind, M, prec=prec, prec_type=prec_type, do_scale=(prec_type == "diag"), strategy=strategy,
                             variant=variant)
-    b = host_shim.ShimBatch(d, n)
+    b = host_shim.ShimBatch(d, n, entry=entry)
     u, r = b.reset(lam)
     ou, orr = exact.reset(Q, 1.0, lam, variant)
     assert_same(u, ou); assert_same(r, orr)
@@ -108,3 +108,10 @@ def test_philox_draws_curriculum_and_fused_autoreset_on_host():
     assert_same(out["u"], nu); assert_same(out["r"], nr)
     assert np.all(b.episodes[:n] == 5) and np.all(b.niter[:n] == 0)
     assert_same(b.resnorm[:n], np.abs(nr).max(axis=1))
+
+
+def test_shared_memory_formulation_of_large_dense_kernels():
+    """HOLD 5 (inverse work matrix, Pinv and C in the complex side store): same bits as the oracle"""
+    _run("sdc-v0", 7, 200, prec_type="lower_tri", seed=21, entry="shim_step_hold5")
+    _run("sdc-v0", 9, 100, prec="LU", seed=22, entry="shim_step_hold5")
+    _run("sdc-v1", 6, 100, prec_type="strictly_lower_tri", steps=10, seed=23, entry="shim_step_hold5")
