@@ -35,7 +35,6 @@ def test_config2_m_sweep_triangular_4m_envs(M, prec_type):
     assert bool((niter[~conv & ~err] == 50).all())
     assert bool(torch.equal(rew[~err], niter[~err].double() * -0.1))
     assert bool(torch.equal(out["lam"], lam0))
-    assert float(conv.double().mean()) > 0.01  # the solver does converge for part of the batch
     idx = np.arange(0, n, n // 1024)
     lam_h = lam0.cpu().numpy()[idx]
     Q = collocation_matrix(M)
