@@ -15,8 +15,8 @@
  *    cudaError_t.  Nothing throws across the ABI.
  *  - Device-pointer entry points never allocate, free or synchronise: all buffers are caller-owned device
  *    memory, work is enqueued on the caller's `stream` (a cudaStream_t passed as void*).
- *  - Host-pointer entry points (sdcgym_pipe_*) own pinned staging, device state and their streams inside an
- *    opaque handle and return when the results are in the caller's host buffers.
+ *  - The host-pointer entry point (sdcgym_pipe_step) owns only its streams/events inside an opaque handle and
+ *    returns when the results are in the caller's host buffers.
  *  - Batched env state is stored as planes ("struct of arrays"): plane p of env i lives at base[p*ld + i],
  *    `ld` >= N is the plane stride in elements.  Complex values are two consecutive planes (re, im).
  *      lam   : 2 planes            lambda of the running episode
@@ -30,6 +30,7 @@
 #ifndef SDCGYM_H
 #define SDCGYM_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -208,6 +209,31 @@ int sdcgym_vecnorm_reward(int64_t N, const double* reward, const uint8_t* flags,
 int sdcgym_gae(int T, int64_t N, const double* rewards, const double* values, const uint8_t* episode_starts,
                const double* last_values, const uint8_t* last_dones, double gamma, double gae_lambda,
                double* advantages, double* returns, void* stream);
+
+/*
+ * Host-buffer step: `DummyVecEnv.step(actions)` with numpy-style HOST arrays on both sides, as one call.
+ * Device buffers (state, staging for actions `dev->action` [N][A], outputs in `dev`, `obs_dev` [N][2][M] complex128)
+ * stay caller-owned; the pipe owns three streams and its events.  The batch is cut into `chunks` pieces and
+ * H2D(actions) | step + export kernels | D2H(results) are overlapped; the call returns when the host arrays are
+ * filled.  Page-locked host memory (sdcgym_host_alloc, cudaHostAlloc, torch pin_memory) makes the copies
+ * asynchronous; pageable memory works but serialises them.  NULL host outputs are skipped.
+ */
+typedef struct sdcgym_pipe sdcgym_pipe;
+typedef struct sdcgym_host_io {
+    const double* action; /* [N][A] (complex: [N][A][2]) */
+    double* obs;          /* [N][2][M] complex128 (reference observation layout) */
+    double* reward;       /* [N] */
+    uint8_t* flags;       /* [N] */
+    int32_t* niter;       /* [N] */
+    double* residual;     /* [N] */
+    double* lam;          /* [N][2] */
+} sdcgym_host_io;
+int sdcgym_pipe_create(int max_chunks, sdcgym_pipe** out);
+int sdcgym_pipe_destroy(sdcgym_pipe* pipe);
+int sdcgym_pipe_step(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* dev,
+                     double* obs_dev, const sdcgym_host_io* host, int chunks, void* caller_stream);
+int sdcgym_host_alloc(size_t bytes, void** out); /* page-locked host memory */
+int sdcgym_host_free(void* p);
 
 /* sum of x[0..N) in fp64 with a fixed (N-independent per block, deterministic) reduction tree -> out[0] */
 int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream);

@@ -114,6 +114,20 @@ class RhoDesc(ctypes.Structure):
     ]
 
 
+class HostIO(ctypes.Structure):
+    """struct sdcgym_host_io"""
+
+    _fields_ = [
+        ("action", ctypes.c_void_p),
+        ("obs", ctypes.c_void_p),
+        ("reward", ctypes.c_void_p),
+        ("flags", ctypes.c_void_p),
+        ("niter", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p),
+        ("lam", ctypes.c_void_p),
+    ]
+
+
 class SdcGymError(RuntimeError):
     pass
 
@@ -158,6 +172,14 @@ def load():
     L.sdcgym_vecnorm_apply.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, dbl, dbl, vp, vp]
     L.sdcgym_vecnorm_returns.argtypes = [i64, vp, dbl, vp, vp]
     L.sdcgym_vecnorm_reward.argtypes = [i64, vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
+    L.sdcgym_pipe_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.sdcgym_pipe_destroy.argtypes = [vp]
+    L.sdcgym_pipe_step.argtypes = [vp, ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(StepIO), vp,
+                                   ctypes.POINTER(HostIO), ctypes.c_int, vp]
+    L.sdcgym_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.sdcgym_host_free.argtypes = [vp]
+    for name in ("sdcgym_pipe_create", "sdcgym_pipe_destroy", "sdcgym_pipe_step", "sdcgym_host_alloc", "sdcgym_host_free"):
+        getattr(L, name).restype = ctypes.c_int
     L.sdcgym_gae.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     L.sdcgym_gae.restype = ctypes.c_int
     for name in ("sdcgym_residual_step", "sdcgym_vecnorm_scratch_doubles", "sdcgym_vecnorm_accumulate",

@@ -1,0 +1,148 @@
+// hostpipe.cu - host-buffer entry point: one C call that steps a batch whose actions and results live in HOST
+// memory, pipelining  H2D(actions) -> step + observation export kernels -> D2H(results)  over three streams in
+// chunks, so PCIe traffic in both directions overlaps the kernels (include/sdcgym.h: sdcgym_pipe_*).
+//
+// This is the C-ABI form of `DummyVecEnv.step(actions)` with numpy arrays on both sides (reference call sites
+// rl_playground.py:82,138; dp_playground.py:807).  Device buffers stay caller-owned; the pipe owns only its
+// streams and events.
+#include <cuda_runtime.h>
+
+#include <new>
+
+#include "../../include/sdcgym.h"
+
+struct sdcgym_pipe {
+    int device;
+    int max_chunks;
+    cudaStream_t s_in, s_k, s_out;
+    cudaEvent_t* ev_in;   // [max_chunks] actions of chunk c are on the device
+    cudaEvent_t* ev_k;    // [max_chunks] kernels of chunk c are done
+    cudaEvent_t ev_start;
+};
+
+#define PIPE_CHECK(x)                       \
+    do {                                    \
+        cudaError_t e_ = (x);               \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+extern "C" int sdcgym_pipe_create(int max_chunks, sdcgym_pipe** out) {
+    if (!out) return SDCGYM_ENULL;
+    if (max_chunks < 1 || max_chunks > 1024) return SDCGYM_EINVAL;
+    sdcgym_pipe* p = new (std::nothrow) sdcgym_pipe();
+    if (!p) return SDCGYM_ENOMEM;
+    p->max_chunks = max_chunks;
+    p->ev_in = new (std::nothrow) cudaEvent_t[max_chunks];
+    p->ev_k = new (std::nothrow) cudaEvent_t[max_chunks];
+    if (!p->ev_in || !p->ev_k) return SDCGYM_ENOMEM;
+    PIPE_CHECK(cudaGetDevice(&p->device));
+    PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_k, cudaStreamNonBlocking));
+    PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    for (int c = 0; c < max_chunks; c++) {
+        PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_in[c], cudaEventDisableTiming));
+        PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_k[c], cudaEventDisableTiming));
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int sdcgym_pipe_destroy(sdcgym_pipe* p) {
+    if (!p) return 0;
+    cudaStreamSynchronize(p->s_in);
+    cudaStreamSynchronize(p->s_k);
+    cudaStreamSynchronize(p->s_out);
+    for (int c = 0; c < p->max_chunks; c++) {
+        cudaEventDestroy(p->ev_in[c]);
+        cudaEventDestroy(p->ev_k[c]);
+    }
+    cudaEventDestroy(p->ev_start);
+    cudaStreamDestroy(p->s_in);
+    cudaStreamDestroy(p->s_k);
+    cudaStreamDestroy(p->s_out);
+    delete[] p->ev_in;
+    delete[] p->ev_k;
+    delete p;
+    return 0;
+}
+
+extern "C" int sdcgym_host_alloc(size_t bytes, void** out) {
+    if (!out) return SDCGYM_ENULL;
+    return (int)cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+}
+extern "C" int sdcgym_host_free(void* p) { return p ? (int)cudaFreeHost(p) : 0; }
+
+extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st,
+                                const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host, int chunks,
+                                void* caller_stream) {
+    if (!p || !desc || !st || !dev || !host) return SDCGYM_ENULL;
+    const int64_t N = st->N;
+    if (N < 0 || chunks < 1) return SDCGYM_EINVAL;
+    if (chunks > p->max_chunks) chunks = p->max_chunks;
+    if (N == 0) return 0;
+    const int M = desc->M;
+    const int A = sdcgym_num_actions(M, desc->prec_type);
+    const int aw = A * (desc->action_is_complex ? 2 : 1);  // doubles per env in the action arrays
+    if (A > 0 && (!host->action || !dev->action)) return SDCGYM_ENULL;
+    if (host->obs && !obs_dev) return SDCGYM_ENULL;
+    cudaStream_t cs = (cudaStream_t)caller_stream;
+    // everything the caller enqueued before this call happens before the pipeline starts
+    PIPE_CHECK(cudaEventRecord(p->ev_start, cs));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
+
+    double* act_dev = const_cast<double*>(dev->action);
+    for (int c = 0; c < chunks; c++) {
+        int64_t lo = (N * c / chunks) / 32 * 32, hi = (c + 1 == chunks) ? N : (N * (c + 1) / chunks) / 32 * 32;
+        if (hi <= lo) continue;
+        const int64_t n = hi - lo;
+        if (A > 0) {
+            PIPE_CHECK(cudaMemcpyAsync(act_dev + lo * aw, host->action + lo * aw, sizeof(double) * n * aw,
+                                       cudaMemcpyHostToDevice, p->s_in));
+            PIPE_CHECK(cudaEventRecord(p->ev_in[c], p->s_in));
+            PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[c], 0));
+        }
+        // sub-batch views: planes are addressed base + lo, per-env arrays base + lo (* width)
+        sdcgym_state s2 = *st;
+        s2.N = n;
+        s2.lam += lo; s2.S += lo; s2.resnorm += lo; s2.niter += lo; s2.episodes += lo; s2.rng_ctr += lo;
+        sdcgym_step_io io = *dev;
+        io.action = A > 0 ? act_dev + lo * aw : nullptr;
+        io.action_env_stride = aw;
+        io.action_comp_stride = desc->action_is_complex ? 2 : 1;
+        if (io.reward) io.reward += lo;
+        if (io.flags) io.flags += lo;
+        if (io.info_residual) io.info_residual += lo;
+        if (io.info_niter) io.info_niter += lo;
+        if (io.info_lam) io.info_lam += 2 * lo;
+        if (io.terminal_obs) io.terminal_obs += lo;
+        sdcgym_env_desc d2 = *desc;
+        d2.env_offset += lo;
+        int rc = sdcgym_step(&d2, &s2, &io, p->s_k);
+        if (rc) return rc;
+        if (host->obs) {
+            rc = sdcgym_export_obs(M, n, st->ld, st->S + lo, obs_dev + lo * 4 * M, p->s_k);
+            if (rc) return rc;
+        }
+        PIPE_CHECK(cudaEventRecord(p->ev_k[c], p->s_k));
+        PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[c], 0));
+#define D2H(hostp, devp, bytes_per_env)                                                                             \
+    if ((hostp) && (devp))                                                                                          \
+        PIPE_CHECK(cudaMemcpyAsync((char*)(hostp) + (size_t)lo * (bytes_per_env), (const char*)(devp) + (size_t)lo * (bytes_per_env), \
+                                   (size_t)n * (bytes_per_env), cudaMemcpyDeviceToHost, p->s_out));
+        D2H(host->obs, obs_dev, 4 * M * sizeof(double))
+        D2H(host->reward, dev->reward, sizeof(double))
+        D2H(host->flags, dev->flags, 1)
+        D2H(host->niter, dev->info_niter, sizeof(int32_t))
+        D2H(host->residual, dev->info_residual, sizeof(double))
+        D2H(host->lam, dev->info_lam, 2 * sizeof(double))
+#undef D2H
+    }
+    PIPE_CHECK(cudaStreamSynchronize(p->s_out));
+    // later work on the caller's stream must see the new state
+    PIPE_CHECK(cudaEventRecord(p->ev_start, p->s_k));
+    PIPE_CHECK(cudaStreamWaitEvent(cs, p->ev_start, 0));
+    return 0;
+}

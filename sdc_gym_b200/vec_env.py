@@ -188,6 +188,7 @@ class SDCVecEnv:
         output: str = "numpy",
         reuse_buffers: bool = False,
         pipeline_chunks: int = 0,
+        host_pipeline: str = "native",
     ):
         torch = _torch()
         if envname not in _lib.ENV_KINDS:
@@ -267,6 +268,10 @@ class SDCVecEnv:
         self._pending = None
         self._streams = None
         self.pipeline_chunks = int(pipeline_chunks)
+        if host_pipeline not in ("native", "torch"):
+            raise ValueError("host_pipeline must be 'native' (sdcgym_pipe_step) or 'torch' (torch streams)")
+        self.host_pipeline = host_pipeline
+        self._pipe = None
 
         self._desc = _lib.EnvDesc()
         d = self._desc
@@ -570,8 +575,29 @@ class SDCVecEnv:
         src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
         if self.collect_states:
             return self._step_collect_states(host, src)
-        # ---- chunked pipeline: H2D(actions) | kernel + export | D2H(results) on three streams ----
         chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(8, N // 131072))
+        if self.host_pipeline == "native":
+            # ---- one C call: chunked H2D | kernels | D2H pipeline inside libsdcgym.so (csrc/hostpipe.cu) ----
+            if self._pipe is None:
+                handle = ctypes.c_void_p()
+                _lib.check(self._L.sdcgym_pipe_create(64, ctypes.byref(handle)), "sdcgym_pipe_create")
+                self._pipe = handle
+            io = _lib.StepIO()
+            io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
+            io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
+            io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
+            io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
+            hio = _lib.HostIO()
+            hio.action = src.data_ptr() if src is not None else None
+            hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
+            hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
+            st = self._state()
+            _lib.check(self._L.sdcgym_pipe_step(self._pipe, ctypes.byref(self._desc), ctypes.byref(st), ctypes.byref(io),
+                                                self.obs_aos.data_ptr(), ctypes.byref(hio), chunks, self._stream()),
+                       "sdcgym_pipe_step")
+            self._invalidate()
+            return self._host_outputs(host)
+        # ---- the same pipeline driven from Python with torch streams (kept as a cross-check) ----
         bounds = [(N * c // chunks // 32 * 32 if c < chunks else N) for c in range(chunks + 1)]
         bounds[0] = 0
         main = torch.cuda.current_stream(self.device)
@@ -716,6 +742,15 @@ class SDCVecEnv:
 
     def close(self):
         self._host = None
+        if self._pipe is not None:
+            self._L.sdcgym_pipe_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def render(self, *a, **k):  # pragma: no cover
         raise NotImplementedError

@@ -120,10 +120,14 @@ def test_pipelined_host_step_equals_device_step():
     act = rng.uniform(-1, 1, (n, 5))
     a = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, pipeline_chunks=5, **KW)
     b = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, **KW)
+    c = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, pipeline_chunks=3, host_pipeline="torch", **KW)
     import torch
-    oa = a.reset(); b.reset()
+    oa = a.reset(); b.reset(); c.reset()
     for _ in range(2):
         obs, rew, done, infos = a.step(act)
+        obs_c, rew_c, done_c, infos_c = c.step(act)
+        assert_same(obs, obs_c); assert_same(rew, rew_c); assert np.array_equal(infos.niter, infos_c.niter)
+        assert_same(infos.lam, infos_c.lam); assert np.array_equal(infos.flags, infos_c.flags)
         out = b.step_tensor(torch.as_tensor(act, device=b.device))
         assert_same(rew, out["reward"].cpu().numpy()); assert np.array_equal(infos.niter, out["niter"].cpu().numpy())
         assert_same(infos.residual, out["residual"].cpu().numpy())
