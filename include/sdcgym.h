@@ -169,6 +169,15 @@ int sdcgym_spectral_radius(const sdcgym_rho_desc* desc, int64_t N, const double*
                            void* stream);
 
 /*
+ * rho and its gradient with respect to the Q_delta parameters (what jax.value_and_grad(loss) evaluates,
+ * dp_playground.py:1073, for the spectral-radius loss): grad[N][A][2] receives g (complex, interleaved) with
+ * d rho = Re(sum_k g_k d theta_k); for real parameters d rho / d theta_k = Re g_k.  lam / qd as in
+ * sdcgym_spectral_radius (no grid / broadcast mode).  Valid where the dominant eigenvalue is simple.
+ */
+int sdcgym_spectral_radius_grad(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, double* rho,
+                                double* grad, void* stream);
+
+/*
  * ResidualLoss.take_step (dp_playground.py:247-258) for N samples: u' = u + inv(I - lam*dt*Qd) r_old,
  * r' = u0 - C u', norm = ||r'||_inf.  lam [N], u0/u/r_old/u_out/r_out [N][M] complex128 interleaved,
  * qd as in sdcgym_spectral_radius, Cs [N][M][M] complex128 or NULL (then C = I - lam*dt*Q is formed on the fly).

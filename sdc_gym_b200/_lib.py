@@ -164,6 +164,8 @@ def load():
     L.sdcgym_fp64_peak_probe.argtypes = [i64, vp, _c_double_p, vp]
     if hasattr(L, "sdcgym_spectral_radius"):
         L.sdcgym_spectral_radius.argtypes = [ctypes.POINTER(RhoDesc), i64, vp, vp, vp, vp]
+    L.sdcgym_spectral_radius_grad.argtypes = [ctypes.POINTER(RhoDesc), i64, vp, vp, vp, vp, vp]
+    L.sdcgym_spectral_radius_grad.restype = ctypes.c_int
     dp_ = ctypes.POINTER(RhoDesc)
     L.sdcgym_residual_step.argtypes = [dp_, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_scratch_doubles.argtypes = [ctypes.c_int]

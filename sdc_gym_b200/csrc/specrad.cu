@@ -12,6 +12,21 @@ __global__ void __launch_bounds__(128, (M <= 5) ? SDCGYM_RHO_MINB : 1) rho_kerne
 }
 
 template <int M>
+__global__ void __launch_bounds__(128, (M <= 5) ? 2 : 1) rho_grad_kernel(const __grid_constant__ RhoParams<M> p,
+                                                                        double* __restrict__ grad) {
+    rho_grad_one<M>(p, (int64_t)blockIdx.x * 128 + threadIdx.x, grad);
+}
+
+template <int M>
+static int launch_rho_grad(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, double* rho,
+                           double* grad, cudaStream_t s) {
+    RhoParams<M> p;
+    fill_rho_params<M>(p, d, N, lam, qd, rho);
+    rho_grad_kernel<M><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(p, grad);
+    return (int)cudaGetLastError();
+}
+
+template <int M>
 static int launch_rho(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, double* rho,
                       cudaStream_t s) {
     RhoParams<M> p;
@@ -41,6 +56,23 @@ extern "C" int sdcgym_spectral_radius(const sdcgym_rho_desc* d, int64_t N, const
     cudaStream_t s = (cudaStream_t)stream;
     switch (d->M) {
 #define C(m) case m: return launch_rho<m>(d, N, lam, qd, rho, s);
+        C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)
+#undef C
+    }
+    return SDCGYM_EUNSUPPORTED;
+}
+
+extern "C" int sdcgym_spectral_radius_grad(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd,
+                                           double* rho, double* grad, void* stream) {
+    if (!d) return SDCGYM_ENULL;
+    if (!sdcgym_supported(d->M, d->prec_type)) return SDCGYM_EUNSUPPORTED;
+    if (d->prec_type == SDCGYM_PREC_FIXED) return SDCGYM_EUNSUPPORTED;  // nothing to differentiate
+    if (N < 0 || d->qd_broadcast) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!lam || !qd || !rho || !grad) return SDCGYM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (d->M) {
+#define C(m) case m: return launch_rho_grad<m>(d, N, lam, qd, rho, grad, s);
         C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)
 #undef C
     }

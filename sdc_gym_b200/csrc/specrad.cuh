@@ -55,7 +55,7 @@ SDCGYM_HD C2 c_sqrt(C2 a) {  // principal square root
 
 // eigenvalue modulus maximum of the M x M complex matrix H (row-major, destroyed)
 template <int M>
-SDCGYM_HD double max_abs_eig(C2 (&H)[M * M]) {
+SDCGYM_HD double max_abs_eig(C2 (&H)[M * M], C2* mu_out = nullptr) {
 #define H_(i, j) H[(i) * M + (j)]
     // ---- Householder reduction to upper Hessenberg form ----
 #pragma unroll
@@ -106,6 +106,7 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M]) {
     // ---- shifted QR on the Hessenberg matrix, deflating from the bottom ----
     const double eps = 2.220446049250313e-16;
     double rho = 0.0;
+    C2 mu_max{0.0, 0.0};
     int hi = M - 1;
     int its = 0;
     bool failed = false;
@@ -123,6 +124,7 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M]) {
         double scale = c_abs1(d0) + c_abs1(d1);
         if (c_abs1(sub) <= eps * scale || c_abs1(sub) == 0.0) {
             double a = sqrt(c_abs2(d1));
+            if (a > rho) mu_max = d1;
             rho = a > rho ? a : rho;
             hi--;
             its = 0;
@@ -192,6 +194,8 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M]) {
     }
     if (failed || hi > 0) return d_nan();
     double a = sqrt(c_abs2(H_(0, 0)));
+    if (a > rho) mu_max = H_(0, 0);
+    if (mu_out) *mu_out = mu_max;
     return a > rho ? a : rho;
 #undef H_
 }
@@ -218,6 +222,165 @@ SDCGYM_HD double spectral_radius_one(const double* Q, double zr, double zi, cons
 #pragma unroll
     for (int k = 0; k < M * M; k++) X[k] = c_mul(z, X[k]);
     return max_abs_eig<M>(X);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gradient of rho with respect to the Q_delta entries (what jax.value_and_grad(loss) needs,
+// dp_playground.py:1073).  For a simple dominant eigenvalue mu with right / left eigenvectors x, y:
+//     d mu = y^H dK x / (y^H x),        K = z P^{-1} (Q - Qd),  P = I - z Qd
+//     dK   = z P^{-1} dQd (K - I)       =>  d mu / d Qd_ij = z conj(w_i) (mu - 1) x_j / (y^H x),   w = P^{-H} y
+//     d rho = Re( conj(mu)/|mu| d mu )  =>  g_ij = conj(mu)/|mu| * d mu / d Qd_ij   (d rho = Re(sum g_ij dQd_ij))
+// Eigenvectors come from two steps of inverse iteration on (K - mu' I) with a slightly perturbed shift; the LU
+// with partial pivoting is unrolled with predicated row swaps so everything stays in registers for small M.
+// ---------------------------------------------------------------------------------------------------------
+template <int M>
+SDCGYM_HD void lu_factor(C2 (&A)[M * M], int (&piv)[M]) {
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        int p = k;
+        double best = c_abs1(A[k * M + k]);
+#pragma unroll
+        for (int i = k + 1; i < M; i++) {
+            const double v = c_abs1(A[i * M + k]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        piv[k] = p;
+#pragma unroll
+        for (int q = k + 1; q < M; q++) {
+            const bool sw = (p == q);
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                const C2 t = A[k * M + c];
+                A[k * M + c] = sw ? A[q * M + c] : t;
+                A[q * M + c] = sw ? t : A[q * M + c];
+            }
+        }
+        C2 d = A[k * M + k];
+        if (c_abs2(d) == 0.0) d = C2{1e-300, 0.0};  // exactly singular shift: any tiny pivot does for inverse iteration
+        A[k * M + k] = d;
+        const C2 inv = c_div(C2{1.0, 0.0}, d);
+#pragma unroll
+        for (int i = k + 1; i < M; i++) {
+            const C2 l = c_mul(A[i * M + k], inv);
+            A[i * M + k] = l;
+#pragma unroll
+            for (int c = k + 1; c < M; c++) A[i * M + c] = c_sub(A[i * M + c], c_mul(l, A[k * M + c]));
+        }
+    }
+}
+template <int M>
+SDCGYM_HD void lu_solve(const C2 (&A)[M * M], const int (&piv)[M], C2 (&b)[M]) {
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+#pragma unroll
+        for (int q = k + 1; q < M; q++) {
+            const bool sw = (piv[k] == q);
+            const C2 t = b[k];
+            b[k] = sw ? b[q] : t;
+            b[q] = sw ? t : b[q];
+        }
+#pragma unroll
+        for (int i = k + 1; i < M; i++) b[i] = c_sub(b[i], c_mul(A[i * M + k], b[k]));
+    }
+#pragma unroll
+    for (int k = M - 1; k >= 0; k--) {
+#pragma unroll
+        for (int c = k + 1; c < M; c++) b[k] = c_sub(b[k], c_mul(A[k * M + c], b[c]));
+        b[k] = c_div(b[k], A[k * M + k]);
+    }
+}
+template <int M>
+SDCGYM_HD void normalize_vec(C2 (&v)[M]) {
+    double m = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; i++) m = fmax(m, c_abs1(v[i]));
+    const double s = (m > 0.0 && m < 1e300) ? 1.0 / m : 1.0;
+#pragma unroll
+    for (int i = 0; i < M; i++) v[i] = c_scale(v[i], s);
+}
+
+// rho and its gradient: grad[(i*M + j)] = g_ij (complex), for the structurally non-zero (lower-triangular) entries.
+template <int M>
+SDCGYM_HD double spectral_radius_grad_one(const double* Q, double zr, double zi, const C2 (&Qd)[M * M], C2 (&G)[M * M]) {
+    const C2 z{zr, zi};
+    C2 K[M * M], H[M * M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        const C2 inv = c_div(C2{1.0, 0.0}, c_sub(C2{1.0, 0.0}, c_mul(z, Qd[i * M + i])));
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            C2 acc{0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < i; j++) acc = c_add(acc, c_mul(Qd[i * M + j], K[j * M + c]));
+            C2 b = C2{Q[i * M + c], 0.0};
+            if (c <= i) b = c_sub(b, Qd[i * M + c]);
+            K[i * M + c] = c_mul(c_add(b, c_mul(z, acc)), inv);  // K holds X = P^{-1}(Q - Qd) for now
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < M * M; k++) {
+        K[k] = c_mul(z, K[k]);
+        H[k] = K[k];
+    }
+    C2 mu;
+    const double rho = max_abs_eig<M>(H, &mu);
+#pragma unroll
+    for (int k = 0; k < M * M; k++) G[k] = C2{0.0, 0.0};
+    if (!(rho > 1e-300) || rho != rho) return rho;  // mu = 0 (lambda = 0) or failed iteration: zero gradient
+    // shifted matrices: A = K - mu' I (right vector), At = A^H (left vector)
+    const C2 mus = c_mul(mu, C2{1.0 + 3e-11, 2e-11});
+    C2 A[M * M], At[M * M];
+#pragma unroll
+    for (int i = 0; i < M; i++)
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            C2 a = K[i * M + j];
+            if (i == j) a = c_sub(a, mus);
+            A[i * M + j] = a;
+            At[j * M + i] = c_conj(a);
+        }
+    int piv[M], pivt[M];
+    lu_factor<M>(A, piv);
+    lu_factor<M>(At, pivt);
+    C2 x[M], y[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        x[i] = C2{1.0, 0.1 * (i + 1)};
+        y[i] = C2{1.0, -0.1 * (i + 1)};
+    }
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        lu_solve<M>(A, piv, x);
+        normalize_vec<M>(x);
+        lu_solve<M>(At, pivt, y);
+        normalize_vec<M>(y);
+    }
+    // w = P^{-H} y: P^H is upper triangular with entries conj(P_ji); back substitution
+    C2 w[M];
+#pragma unroll
+    for (int i = M - 1; i >= 0; i--) {
+        C2 acc = y[i];
+#pragma unroll
+        for (int j = i + 1; j < M; j++) {
+            // (P^H)_{ij} = conj(P_{ji}) = conj(-z Qd_{ji})
+            acc = c_add(acc, c_mul(c_conj(c_mul(z, Qd[j * M + i])), w[j]));
+        }
+        w[i] = c_div(acc, c_conj(c_sub(C2{1.0, 0.0}, c_mul(z, Qd[i * M + i]))));
+    }
+    C2 yhx{0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < M; i++) yhx = c_add(yhx, c_mul(c_conj(y[i]), x[i]));
+    // common factor: conj(mu)/|mu| * z * (mu - 1) / (y^H x)
+    C2 f = c_mul(c_scale(c_conj(mu), 1.0 / rho), c_mul(z, c_sub(mu, C2{1.0, 0.0})));
+    f = c_div(f, yhx);
+#pragma unroll
+    for (int i = 0; i < M; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) G[i * M + j] = c_mul(f, c_mul(c_conj(w[i]), x[j]));
+    return rho;
 }
 
 }  // namespace sdcgym

@@ -22,9 +22,8 @@ struct RhoParams {
 };
 
 template <int M>
-SDCGYM_HD void rho_one(const RhoParams<M>& p, int64_t i) {
-    if (i >= p.N) return;
-    double lr, li;
+SDCGYM_HD bool rho_inputs(const RhoParams<M>& p, int64_t i, double& lr, double& li, C2 (&Qd)[M * M]) {
+    if (i >= p.N) return false;
     if (p.lam) {
         lr = p.lam[2 * i];
         li = p.lam[2 * i + 1];
@@ -34,7 +33,6 @@ SDCGYM_HD void rho_one(const RhoParams<M>& p, int64_t i) {
         lr = (p.grid_re > 1) ? p.re_lo + (p.re_hi - p.re_lo) * ((double)a / (double)(p.grid_re - 1)) : p.re_lo;
         li = (p.grid_im > 1) ? p.im_lo + (p.im_hi - p.im_lo) * ((double)b / (double)(p.grid_im - 1)) : p.im_lo;
     }
-    C2 Qd[M * M];
     const int w = p.qd_is_complex ? 2 : 1;
     const double* row = p.qd ? p.qd + (p.qd_broadcast ? 0 : i * (int64_t)p.n_act * w) : nullptr;
     int k = 0;
@@ -60,7 +58,45 @@ SDCGYM_HD void rho_one(const RhoParams<M>& p, int64_t i) {
             }
             Qd[r * M + c] = d;
         }
+    return true;
+}
+
+template <int M>
+SDCGYM_HD void rho_one(const RhoParams<M>& p, int64_t i) {
+    double lr, li;
+    C2 Qd[M * M];
+    if (!rho_inputs<M>(p, i, lr, li, Qd)) return;
     p.rho[i] = spectral_radius_one<M>(p.Q, lr * p.dt, li * p.dt, Qd);
+}
+
+// rho and d rho / d(parameter k) for the action layout of prec_type: grad[i][k] = g (complex, interleaved),
+// d rho = Re(sum_k g_k d theta_k); for real parameters the derivative is Re(g_k).
+template <int M>
+SDCGYM_HD void rho_grad_one(const RhoParams<M>& p, int64_t i, double* __restrict__ grad) {
+    double lr, li;
+    C2 Qd[M * M], G[M * M];
+    if (!rho_inputs<M>(p, i, lr, li, Qd)) return;
+    p.rho[i] = spectral_radius_grad_one<M>(p.Q, lr * p.dt, li * p.dt, Qd, G);
+    double* g = grad + i * (int64_t)p.n_act * 2;
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < M; r++)
+#pragma unroll
+        for (int c = 0; c < M; c++) {
+            bool take = false;
+            switch (p.prec_type) {
+            case SDCGYM_PREC_DIAG: take = (c == r); break;
+            case SDCGYM_PREC_LOWER_DIAG: take = (r == c + 1); break;
+            case SDCGYM_PREC_LOWER_TRI: take = (c <= r); break;
+            case SDCGYM_PREC_STRICTLY_LOWER_TRI: take = (c < r); break;
+            default: break;
+            }
+            if (take) {
+                g[2 * k] = G[r * M + c].r;
+                g[2 * k + 1] = G[r * M + c].i;
+                k++;
+            }
+        }
 }
 
 template <int M>

@@ -94,6 +94,53 @@ class SpectralRadiusLoss:
         rho = self.spectral_radii(lams, outputs)
         return self.mean(rho)
 
+    def radii_and_grads(self, lams, outputs):
+        """(rho (B,), g (B, n_out) complex128) with d rho_b = Re(sum_k g_bk d output_bk): per-sample spectral
+        radius and its derivative with respect to the Q_delta parameters (left/right eigenvector formula,
+        ``csrc/specrad.cuh``).  Valid where the dominant eigenvalue is simple."""
+        torch = _torch()
+        if self.prec is not None:
+            raise ValueError("a fixed preconditioner has no parameters to differentiate")
+        lam = lams if isinstance(lams, torch.Tensor) else torch.as_tensor(np.asarray(lams, dtype=np.complex128))
+        lam = lam.detach().to(self.device).to(torch.complex128).reshape(-1).contiguous()
+        B = lam.numel()
+        out = outputs.detach() if isinstance(outputs, torch.Tensor) else outputs
+        qd, is_c, bc = self._outputs_tensor(out, B)
+        if bc:
+            qd = qd.expand(B, *qd.shape[1:]).contiguous()
+        d = self._desc
+        d.qd_is_complex, d.qd_broadcast = is_c, 0
+        d.grid_re = d.grid_im = 0
+        rho = torch.empty(B, dtype=torch.float64, device=self.device)
+        grad = torch.empty((B, self.n_out, 2), dtype=torch.float64, device=self.device)
+        lam_r = torch.view_as_real(lam)
+        _lib.check(self._L.sdcgym_spectral_radius_grad(ctypes.byref(d), B, lam_r.data_ptr(), qd.data_ptr(),
+                                                       rho.data_ptr(), grad.data_ptr(), self._stream()),
+                   "sdcgym_spectral_radius_grad")
+        self._keep = (lam_r, qd)
+        return rho, torch.view_as_complex(grad)
+
+    def value_and_grad(self, lams, outputs, convention="jax"):
+        """(mean rho, d mean_rho / d outputs) - what ``jax.value_and_grad(loss)`` gives the reference's trainer for
+        the loss itself (``dp_playground.py:1038-1073``).  For complex ``outputs`` the gradient follows
+        ``convention``: 'jax' (``d/dx - i d/dy``) or 'torch' (its conjugate); for real outputs it is real."""
+        torch = _torch()
+        rho, g = self.radii_and_grads(lams, outputs)
+        g = g / rho.numel()
+        is_c = (outputs.is_complex() if isinstance(outputs, torch.Tensor) else np.iscomplexobj(outputs))
+        if not is_c:
+            g = g.real
+        elif convention == "torch":
+            g = g.conj()
+        elif convention != "jax":
+            raise ValueError("convention must be 'jax' or 'torch'")
+        return self.mean(rho), g
+
+    def differentiable(self, lams, outputs):
+        """Mean spectral radius as a torch scalar that supports ``.backward()`` into ``outputs`` (a CUDA tensor with
+        ``requires_grad``) - forward and backward both run the hand-written kernels."""
+        return _SpectralRadiusFn.apply(outputs, self, lams)
+
     def mean(self, rho):
         torch = _torch()
         out = torch.empty(1, dtype=torch.float64, device=self.device)
@@ -118,6 +165,36 @@ class SpectralRadiusLoss:
         self._keep = (qd,)
         return rho.reshape(n_re, n_im)
 
+
+def _make_autograd_fn():
+    torch = _torch()
+
+    class SpectralRadiusFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, outputs, loss, lams):
+            value, g = loss.value_and_grad(lams, outputs, convention="torch")
+            ctx.save_for_backward(g)
+            ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
+            return value.reshape(())
+
+        @staticmethod
+        def backward(ctx, upstream):
+            (g,) = ctx.saved_tensors
+            return (g * upstream).reshape(ctx.out_shape).to(ctx.out_dtype), None, None
+
+    return SpectralRadiusFn
+
+
+class _LazyFn:
+    _fn = None
+
+    def apply(self, *a):
+        if _LazyFn._fn is None:
+            _LazyFn._fn = _make_autograd_fn()
+        return _LazyFn._fn.apply(*a)
+
+
+_SpectralRadiusFn = _LazyFn()
 
 NormLoss = SpectralRadiusLoss  # the reference keeps this alias (dp_playground.py:233)
 

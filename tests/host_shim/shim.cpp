@@ -199,3 +199,21 @@ extern "C" int shim_cinv(int M, const double* P, double* out, int variant) {
     }
     return -2;
 }
+
+template <int M>
+static int rho_grad_m(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, double* rho, double* grad) {
+    RhoParams<M> p;
+    fill_rho_params<M>(p, d, N, lam, qd, rho);
+    for (int64_t i = 0; i < N; i++) rho_grad_one<M>(p, i, grad);
+    return 0;
+}
+extern "C" int shim_spectral_radius_grad(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd,
+                                         double* rho, double* grad) {
+    switch (d->M) {
+    case 2: return rho_grad_m<2>(d, N, lam, qd, rho, grad);
+    case 3: return rho_grad_m<3>(d, N, lam, qd, rho, grad);
+    case 5: return rho_grad_m<5>(d, N, lam, qd, rho, grad);
+    case 7: return rho_grad_m<7>(d, N, lam, qd, rho, grad);
+    }
+    return -2;
+}

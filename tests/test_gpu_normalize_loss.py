@@ -185,3 +185,41 @@ def test_gae_kernel_and_rollout_collection():
     assert torch.allclose(b.values, b.observations[:, 0] * 0.1)
     b2 = collect_rollouts(env, policy, 24, buffer=b)  # continues the episodes
     assert b2 is b and not bool(b.episode_starts[0].all())
+
+
+def test_spectral_radius_value_and_grad_and_autograd():
+    import torch
+    from sdc_gym_b200.loss import SpectralRadiusLoss
+    M, B = 5, 4096
+    rng = np.random.default_rng(8)
+    Q = collocation_matrix(M)
+    lam = rng.uniform(-100, 0, B) + 1j * rng.uniform(-10, 0, B)
+    for pt in ("diag", "lower_tri"):
+        A = num_actions(M, pt)
+        loss = SpectralRadiusLoss(M, 1.0, pt)
+        out = rng.uniform(0.05, 0.3, (B, A)) + 1j * rng.uniform(-0.05, 0.05, (B, A))
+        val, g = loss.value_and_grad(lam.reshape(-1, 1), out)  # JAX convention
+        rho = loss.spectral_radii(lam, out)
+        assert abs(float(val) - float(rho.mean())) <= 1e-13 * float(val)
+        g = g.cpu().numpy()
+        # directional derivative of the mean loss along a random complex direction
+        dirv = rng.normal(size=(B, A)) + 1j * rng.normal(size=(B, A))
+        h = 1e-7
+        fp = float(loss(lam, out + h * dirv)); fm = float(loss(lam, out - h * dirv))
+        assert abs((fp - fm) / (2 * h) - np.real(np.sum(g * dirv))) <= 2e-6 * abs(np.real(np.sum(g * dirv)))
+        # torch autograd: real parameters and complex parameters
+        o_c = torch.as_tensor(out, device="cuda").requires_grad_(True)
+        loss.differentiable(torch.as_tensor(lam, device="cuda"), o_c).backward()
+        assert np.allclose(o_c.grad.cpu().numpy(), np.conj(g), rtol=1e-12, atol=1e-15)
+        o_r = torch.as_tensor(out.real.copy(), device="cuda").requires_grad_(True)
+        v = loss.differentiable(torch.as_tensor(lam, device="cuda"), o_r)
+        (3.0 * v).backward()
+        _, g_r = loss.value_and_grad(lam, out.real.copy())
+        assert np.allclose(o_r.grad.cpu().numpy(), 3.0 * g_r.cpu().numpy(), rtol=1e-12, atol=1e-15)
+        assert o_r.grad.dtype == torch.float64 and not g_r.is_complex()
+    # one gradient-descent step on the MIN-like diagonal lowers the loss (sanity of the sign convention)
+    loss = SpectralRadiusLoss(M, 1.0, "diag")
+    d0 = np.tile(np.full(M, 0.3), (B, 1))
+    v0, g0 = loss.value_and_grad(lam, d0)
+    v1 = float(loss(lam, d0 - 0.05 * g0.cpu().numpy() * B))
+    assert v1 < float(v0)

@@ -115,3 +115,58 @@ def test_shared_memory_formulation_of_large_dense_kernels():
     _run("sdc-v0", 7, 200, prec_type="lower_tri", seed=21, entry="shim_step_hold5")
     _run("sdc-v0", 9, 100, prec="LU", seed=22, entry="shim_step_hold5")
     _run("sdc-v1", 6, 100, prec_type="strictly_lower_tri", steps=10, seed=23, entry="shim_step_hold5")
+
+
+def test_spectral_radius_gradient_against_eigenvector_formula_and_finite_differences():
+    """host build of the gradient template: analytic reference from scipy's left/right eigenvectors (1e-8) and
+    central finite differences (1e-5)"""
+    import ctypes
+    import scipy.linalg
+    from sdc_gym_b200 import _lib
+    from sdc_gym_b200.precond import qdmat_from_output
+    L = host_shim.shim()
+    L.shim_spectral_radius_grad.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64] + [ctypes.c_void_p] * 4
+    rng = np.random.default_rng(0)
+
+    def K_of(Q, lam, Qd):
+        M = Q.shape[0]
+        return lam * np.linalg.inv(np.eye(M) - lam * Qd) @ (Q - Qd)
+
+    for M in (3, 5, 7):
+        Q = collocation_matrix(M)
+        for pt, hi in (("diag", 0.4), ("lower_diag", 0.4), ("lower_tri", 0.3), ("strictly_lower_tri", 0.08)):
+            A, n = num_actions(M, pt), 24
+            lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+            qd = rng.uniform(0.02, hi, (n, A)) + 1j * rng.uniform(-0.05, 0.05, (n, A))
+            d = _lib.RhoDesc()
+            d.M, d.prec_type, d.dt, d.qd_is_complex = M, _lib.PREC_TYPES[pt], 1.0, 1
+            for k, v in enumerate(Q.reshape(-1)):
+                d.Q[k] = v
+            rho, g = np.zeros(n), np.zeros((n, A), np.complex128)
+            assert L.shim_spectral_radius_grad(ctypes.byref(d), n, lam.ctypes.data, qd.ctypes.data, rho.ctypes.data,
+                                               g.ctypes.data) == 0
+            for i in range(n):
+                Qd = qdmat_from_output(qd[i], M, pt)
+                K = K_of(Q, lam[i], Qd)
+                w, vl, vr = scipy.linalg.eig(K, left=True, right=True)
+                k = int(np.argmax(abs(w)))
+                mu, x, y = w[k], vr[:, k], vl[:, k]
+                assert abs(rho[i] - abs(mu)) <= 1e-10 * abs(mu)
+                P = np.eye(M) - lam[i] * Qd
+                wv = np.linalg.solve(P.conj().T, y)
+                full = np.conj(mu) / abs(mu) * lam[i] * (mu - 1) * np.outer(np.conj(wv), x) / (np.conj(y) @ x)
+                ref = np.array([full[r, c] for r in range(M) for c in range(M)
+                                if qdmat_from_output(np.arange(1, A + 1), M, pt)[r, c] != 0])
+                # huge gradients flag an ill-conditioned eigenproblem: LAPACK's own vectors are only that good
+                rtol = 1e-7 if abs(ref).max() < 1e4 else 1e-4
+                assert np.allclose(g[i], ref, rtol=rtol, atol=1e-9 * abs(ref).max()), (M, pt, i)
+            # finite differences on one sample
+            i, h = 0, 1e-6
+            for k in range(A):
+                for dirc in (1.0, 1j):
+                    qp, qm = qd[i].copy(), qd[i].copy()
+                    qp[k] += h * dirc
+                    qm[k] -= h * dirc
+                    fp = max(abs(np.linalg.eigvals(K_of(Q, lam[i], qdmat_from_output(qp, M, pt)))))
+                    fm = max(abs(np.linalg.eigvals(K_of(Q, lam[i], qdmat_from_output(qm, M, pt)))))
+                    assert abs((fp - fm) / (2 * h) - (g[i, k] * dirc).real) <= 1e-4 * max(1.0, abs(g[i]).max())
