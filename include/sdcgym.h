@@ -244,8 +244,11 @@ int sdcgym_pipe_step(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgy
 int sdcgym_host_alloc(size_t bytes, void** out); /* page-locked host memory */
 int sdcgym_host_free(void* p);
 
-/* sum of x[0..N) in fp64 with a fixed (N-independent per block, deterministic) reduction tree -> out[0] */
-int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream);
+/* sum of x[0..N) in fp64 with a fixed (N-independent, deterministic) reduction tree -> out[0].  `scratch` is
+ * caller-owned device memory of sdcgym_sum_scratch_doubles() doubles (so concurrent calls on different streams
+ * do not share state). */
+int sdcgym_sum_scratch_doubles(void);
+int sdcgym_sum_f64(int64_t N, const double* x, double* scratch, double* out, void* stream);
 
 /* Measured-peak helper: runs a dependent-free DFMA chain kernel and returns its FLOP count; time it with
  * events on `stream`.  flops_out may be NULL. */

@@ -160,7 +160,8 @@ def load():
     L.sdcgym_export_obs.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
     L.sdcgym_import_obs.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
     L.sdcgym_refresh_resnorm.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
-    L.sdcgym_sum_f64.argtypes = [i64, vp, vp, vp]
+    L.sdcgym_sum_f64.argtypes = [i64, vp, vp, vp, vp]
+    L.sdcgym_sum_scratch_doubles.restype = ctypes.c_int
     L.sdcgym_fp64_peak_probe.argtypes = [i64, vp, _c_double_p, vp]
     if hasattr(L, "sdcgym_spectral_radius"):
         L.sdcgym_spectral_radius.argtypes = [ctypes.POINTER(RhoDesc), i64, vp, vp, vp, vp]

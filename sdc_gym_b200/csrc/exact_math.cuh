@@ -80,20 +80,19 @@ SDCGYM_HD cplx cmul_blas(cplx a, cplx b) {
 // OpenBLAS complex reciprocal (ztrsm diagonal inverse / zgetf2 pivot), Appendix A step 6.
 template <bool FUSED>
 SDCGYM_HD cplx crecip(cplx p) {
+    // branch-free form of
+    //   |pr| >= |pi| : t = pi/pr, den = 1/(pr*(1+t*t)), inv = (den, -t*den)
+    //   else         : t = pr/pi, den = 1/(pi*(1+t*t)), inv = (t*den, -den)
+    // (same operations on selected operands; -t*den == -(t*den) exactly), so independent reciprocals interleave.
+    const bool first = fabs(p.re) >= fabs(p.im);
+    const double a = first ? p.re : p.im, b = first ? p.im : p.re;
+    const double t = ddiv(b, a);
+    const double tt = FUSED ? dfma(t, t, 1.0) : dadd(1.0, dmul(t, t));
+    const double den = ddiv(1.0, dmul(a, tt));
+    const double td = dmul(t, den);
     cplx inv;
-    if (fabs(p.re) >= fabs(p.im)) {
-        double t = ddiv(p.im, p.re);
-        double tt = FUSED ? dfma(t, t, 1.0) : dadd(1.0, dmul(t, t));
-        double den = ddiv(1.0, dmul(p.re, tt));
-        inv.re = den;
-        inv.im = dmul(-t, den);
-    } else {
-        double t = ddiv(p.re, p.im);
-        double tt = FUSED ? dfma(t, t, 1.0) : dadd(1.0, dmul(t, t));
-        double den = ddiv(1.0, dmul(p.im, tt));
-        inv.re = dmul(t, den);
-        inv.im = -den;
-    }
+    inv.re = first ? den : td;
+    inv.im = first ? -td : -den;
     return inv;
 }
 

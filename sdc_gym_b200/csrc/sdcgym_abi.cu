@@ -74,7 +74,6 @@ __global__ void refresh_resnorm_kernel(int M, int64_t N, int64_t ld, const doubl
 
 // ---- deterministic fp64 sum: fixed 1024-block grid-stride partials, then one block folds them --------
 constexpr int kSumBlocks = 1024, kSumThreads = 256;
-__device__ double g_sum_partials[kSumBlocks];
 
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double sm[kSumThreads / 32];
@@ -87,16 +86,18 @@ __device__ __forceinline__ double block_sum(double v) {
     __syncthreads();
     return v;
 }
-__global__ void __launch_bounds__(kSumThreads) sum_partial_kernel(int64_t N, const double* __restrict__ x) {
+__global__ void __launch_bounds__(kSumThreads) sum_partial_kernel(int64_t N, const double* __restrict__ x,
+                                                                  double* __restrict__ partials) {
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * kSumThreads + threadIdx.x; i < N; i += (int64_t)kSumBlocks * kSumThreads)
         acc += x[i];
     acc = block_sum(acc);
-    if (threadIdx.x == 0) g_sum_partials[blockIdx.x] = acc;
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
-__global__ void __launch_bounds__(kSumThreads) sum_final_kernel(double* __restrict__ out) {
+__global__ void __launch_bounds__(kSumThreads) sum_final_kernel(const double* __restrict__ partials,
+                                                                double* __restrict__ out) {
     double acc = 0.0;
-    for (int i = threadIdx.x; i < kSumBlocks; i += kSumThreads) acc += g_sum_partials[i];
+    for (int i = threadIdx.x; i < kSumBlocks; i += kSumThreads) acc += partials[i];
     acc = block_sum(acc);
     if (threadIdx.x == 0) out[0] = acc;
 }
@@ -212,11 +213,13 @@ extern "C" int sdcgym_refresh_resnorm(int M, int64_t N, int64_t ld, const double
     return (int)cudaGetLastError();
 }
 
-extern "C" int sdcgym_sum_f64(int64_t N, const double* x, double* out, void* stream) {
+extern "C" int sdcgym_sum_scratch_doubles(void) { return kSumBlocks; }
+
+extern "C" int sdcgym_sum_f64(int64_t N, const double* x, double* scratch, double* out, void* stream) {
     if (N < 0) return SDCGYM_EINVAL;
-    if (!out || (N > 0 && !x)) return SDCGYM_ENULL;
-    sum_partial_kernel<<<kSumBlocks, kSumThreads, 0, (cudaStream_t)stream>>>(N, x);
-    sum_final_kernel<<<1, kSumThreads, 0, (cudaStream_t)stream>>>(out);
+    if (!out || !scratch || (N > 0 && !x)) return SDCGYM_ENULL;
+    sum_partial_kernel<<<kSumBlocks, kSumThreads, 0, (cudaStream_t)stream>>>(N, x, scratch);
+    sum_final_kernel<<<1, kSumThreads, 0, (cudaStream_t)stream>>>(scratch, out);
     return (int)cudaGetLastError();
 }
 

@@ -144,7 +144,9 @@ class SpectralRadiusLoss:
     def mean(self, rho):
         torch = _torch()
         out = torch.empty(1, dtype=torch.float64, device=self.device)
-        _lib.check(self._L.sdcgym_sum_f64(rho.numel(), rho.data_ptr(), out.data_ptr(), self._stream()), "sdcgym_sum_f64")
+        scratch = torch.empty(self._L.sdcgym_sum_scratch_doubles(), dtype=torch.float64, device=self.device)
+        _lib.check(self._L.sdcgym_sum_f64(rho.numel(), rho.data_ptr(), scratch.data_ptr(), out.data_ptr(),
+                                          self._stream()), "sdcgym_sum_f64")
         return out[0] / rho.numel()
 
     def grid(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None):

@@ -168,7 +168,8 @@ def test_export_import_roundtrip_refresh_and_sum():
     assert_same(env.resnorm[:n].cpu().numpy(), np.abs(r).max(axis=1))
     x = torch.as_tensor(rng.normal(size=123457), device=env.device)
     out = torch.zeros(1, dtype=torch.float64, device=env.device)
-    _lib.check(L.sdcgym_sum_f64(x.numel(), x.data_ptr(), out.data_ptr(), None), "sum")
+    scratch = torch.zeros(L.sdcgym_sum_scratch_doubles(), dtype=torch.float64, device=env.device)
+    _lib.check(L.sdcgym_sum_f64(x.numel(), x.data_ptr(), scratch.data_ptr(), out.data_ptr(), None), "sum")
     torch.cuda.synchronize()
     assert abs(out.item() - float(np.sum(x.cpu().numpy()))) < 1e-9
 
