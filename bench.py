@@ -34,7 +34,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 
-METRIC = "sdc_env_steps_per_sec"
+METRIC = "SDC env-steps/sec (M=5, diag Qdelta)"
 UNIT = "env-steps/s"
 M = 5
 ENVS_PER_GPU = 1 << 20
@@ -159,7 +159,7 @@ def run_reference(args):
               f"8-env sdc-v0 DummyVecEnv loop with uniform random actions; numpy port of the reference env")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_time / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": WORKLOAD, "host_cores": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -284,7 +284,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "global_envs": world * N, "M": M,
                        "prec_type": "diag", "sharding": f"envs partitioned over {world} GPU(s), no collective on the "
                        "step path; NCCL all-reduce of rollout statistics only",

@@ -170,3 +170,13 @@ def test_haswell_variant_equals_oracle_variant():
         snap = env._snapshot()
         assert_same(snap["obs"][:, 0], u); assert_same(snap["obs"][:, 1], r)
         assert np.array_equal(infos.niter, niter); assert_same(infos.residual, out["resnorm"])
+
+
+@pytest.mark.parametrize("M", [2, 4, 6, 8])
+def test_even_M_all_paths_equal_oracle(M):
+    """collocation sizes without golden vectors: every kernel family against the oracle"""
+    _compare_batch("sdc-v0", M, 3000, mode="uniform", seed=60 + M)
+    _compare_batch("sdc-v0", M, 1500, prec="LU", seed=61 + M)
+    _compare_batch("sdc-v0", M, 1500, prec_type="lower_tri", seed=62 + M)
+    _compare_batch("sdc-v1", M, 1000, mode="uniform", steps=20, seed=63 + M, strategy="residual_change")
+    _compare_batch("sdc-v1", M, 500, prec_type="strictly_lower_tri", cplx=True, steps=8, seed=64 + M)

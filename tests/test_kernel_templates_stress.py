@@ -170,3 +170,11 @@ def test_spectral_radius_gradient_against_eigenvector_formula_and_finite_differe
                     fp = max(abs(np.linalg.eigvals(K_of(Q, lam[i], qdmat_from_output(qp, M, pt)))))
                     fm = max(abs(np.linalg.eigvals(K_of(Q, lam[i], qdmat_from_output(qm, M, pt)))))
                     assert abs((fp - fm) / (2 * h) - (g[i, k] * dirc).real) <= 1e-4 * max(1.0, abs(g[i]).max())
+
+
+@pytest.mark.parametrize("M", [2, 4, 6, 8])
+def test_even_M_on_host(M):
+    _run("sdc-v0", M, 400, mode="uniform", seed=70 + M)
+    _run("sdc-v0", M, 200, prec="LU", seed=71 + M)
+    _run("sdc-v0", M, 200, prec_type="lower_tri", seed=72 + M)
+    _run("sdc-v1", M, 100, mode="uniform", steps=12, strategy="residual_change", seed=73 + M)
