@@ -45,7 +45,7 @@ WORKLOAD = "sdc-v0 full solve, M=5, diag Qdelta (uniform random actions), 2^20 e
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed regions (value + e2e) run."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -211,7 +211,6 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     launches = args.steps  # one step kernel per step (solve + reward + auto-reset fused)
     # statistics of the last step (per-rollout reduction over NCCL, outside the step path)
     niter = env.info_niter[:N].to(torch.float64)
@@ -272,6 +271,7 @@ def run_ours(args):
         checksum += float(rew[0]) + float(obs[0, 1, 0].real)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * N * args.steps / e2e_s
     h2d = N * M * 8
     d2h = N * (2 * M * 16 + 8 + 1 + 4 + 8 + 16)
