@@ -69,6 +69,14 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         SDCGYM_TVS(26, 4, 8, 64)
         SDCGYM_TVS(27, 4, 5, 128)
         SDCGYM_TVS(28, 4, 5, 96)
+        SDCGYM_TVS(30, 6, 4, 128)
+        SDCGYM_TVS(31, 6, 5, 128)
+        SDCGYM_TVS(32, 6, 5, 96)
+        SDCGYM_TVS(33, 6, 6, 64)
+        SDCGYM_TVS(34, 6, 6, 96)
+        SDCGYM_TVS(35, 6, 9, 64)
+        SDCGYM_TVS(36, 6, 7, 64)
+        SDCGYM_TVS(37, 4, 7, 64)
 #undef SDCGYM_TVS
 #undef SDCGYM_TV
         default: break;

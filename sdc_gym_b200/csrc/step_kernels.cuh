@@ -373,6 +373,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     }
 
     // ---- system matrix (optionally register resident) ----
+    // experimental residency (tuning only): 6 = Re(C) in shared memory and Im(C) re-derived
     constexpr int NCR = (HOLD >= 1 && HOLD <= 3) ? M * M : 1, NCI = (HOLD == 2) ? M * M : 1;
     double Cr[NCR], Ci[NCI];
     if (HOLD >= 1) {
@@ -387,6 +388,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
                 if (HOLD == 3 || HOLD == 4) side[(r * M + c) * side_stride] = -dmul(zi, q);
                 if (HOLD == 5) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
+                if (HOLD == 6) side[(r * M + c) * side_stride] = crv;
             }
     }
 
@@ -419,7 +421,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         (void)vside;
         (void)vp;
 #ifdef __CUDA_ARCH__
-        if (HOLD < 2) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
+        if (HOLD < 2 || HOLD == 6) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
 #endif
         double dr[M], di[M];
 #pragma unroll
@@ -453,10 +455,12 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             for (int c = 0; c < M; c++) {
                 double q = p.Q[m * M + c];
                 if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
+                else if (HOLD == 6) cr[c] = vside[(m * M + c) * side_stride];
                 else if (HOLD == 4) cr[c] = vside[(M * M + m * M + c) * side_stride];
                 else if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
                 if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
+                else if (HOLD == 6) ci[c] = -dmul(zi_s, q);
                 else if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
                 else if (HOLD >= 3) ci[c] = vside[(m * M + c) * side_stride];
                 else ci[c] = -dmul(zi_s, q);
@@ -606,7 +610,8 @@ template <int M, int HOLD, int BLOCK = kBlock>
 constexpr size_t step_kernel_smem_bytes() {
     return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double)
                      : (HOLD == 4 ? (size_t)2 * M * M * BLOCK * sizeof(double)
-                                  : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double) : 0));
+                                  : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double)
+                                               : (HOLD == 6 ? (size_t)M * M * BLOCK * sizeof(double) : 0)));
 }
 #endif
 
