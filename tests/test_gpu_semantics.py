@@ -295,6 +295,12 @@ def test_ragged_batch_sizes_and_extreme_M(n, M):
         snap = env._snapshot()
         assert_same(snap["obs"][:, 0], u); assert_same(snap["obs"][:, 1], r)
         assert np.array_equal(infos.niter, nit) and done.all()
+    # compute-sanitizer is closed on this pool: the padding [n, ld) of every plane doubles as a canary region
+    for name in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr", "reward", "flags", "info_residual",
+                 "info_niter", "terminal"):
+        t = getattr(env, name)
+        assert bool((t[..., n:] == 0).all()), f"{name}: write beyond the batch"
+    assert bool((env.info_lam[n:] == 0).all())
 
 
 def test_unsupported_configurations_fail_loudly():
