@@ -37,7 +37,7 @@ def main(argv=None):
         loss = loss_fn.differentiable(lam, theta.expand(args.batch, args.M))
         loss.backward()
         opt.step()
-        history.append(float(loss))
+        history.append(float(loss.detach()))
         if step % 50 == 0 or step == args.steps - 1:
             print(f"step {step:4d}  mean rho {history[-1]:.6f}  diag {theta.detach().cpu().numpy().round(4)}")
     return history, theta.detach().cpu().numpy()
