@@ -334,7 +334,8 @@ class SDCVecEnv:
         """DummyVecEnv.seed: env i gets ``seed + i`` in the reference; here one Philox key for the batch."""
         self._desc.seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
         self.rng_ctr.zero_()
-        return [None if seed is None else seed + i for i in range(min(self.num_envs, 64))]
+        # DummyVecEnv returns the per-env seeds; a lazy range instead of a list of num_envs integers
+        return [None] * self.num_envs if seed is None else range(int(seed), int(seed) + self.num_envs)
 
     def set_num_episodes(self, num_episodes, indices=None):
         if indices is None:
@@ -563,6 +564,11 @@ class SDCVecEnv:
         """(obs, rewards, dones, infos) like ``DummyVecEnv.step`` over the reference envs."""
         torch = _torch()
         if self.output == "torch" or (actions is not None and isinstance(actions, torch.Tensor) and actions.is_cuda):
+            if self._kernel_n_act and not isinstance(actions, torch.Tensor):
+                arr = np.asarray(actions, dtype=np.complex128 if self.free_action_space else np.float64)
+                actions = torch.as_tensor(np.ascontiguousarray(arr.reshape(self.num_envs, self._kernel_n_act)))
+            if self._kernel_n_act and not actions.is_cuda:
+                actions = actions.to(self.device)
             out = self.step_tensor(actions if self._kernel_n_act else None)
             obs = self.observation_tensor()
             dones = (out["flags"] & _lib.FLAG_DONE).bool()

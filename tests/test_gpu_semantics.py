@@ -352,3 +352,31 @@ def test_curriculum_lambda_interval():
     env.set_num_episodes(100)
     env.reset()
     assert np.array(env.get_attr("lam")).real.min() < -90
+
+
+def test_torch_output_mode_and_seed_contract():
+    import torch
+    n = 257
+    env = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=4, output="torch", **KW)
+    ref = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=4, **KW)
+    o_t, o_n = env.reset(), ref.reset()
+    assert o_t.is_cuda and o_t.dtype == torch.complex128 and o_t.shape == (n, 2, 5)
+    assert_same(o_t.cpu().numpy(), o_n)
+    act = np.random.default_rng(0).uniform(-1, 1, (n, 5))
+    for a in (act, torch.as_tensor(act), torch.as_tensor(act, device="cuda")):  # numpy, CPU tensor, CUDA tensor
+        obs, rew, done, info = env.step(a)
+        obs_n, rew_n, done_n, info_n = ref.step(act)
+        assert obs.is_cuda and rew.is_cuda and done.dtype == torch.bool
+        assert_same(obs.cpu().numpy(), obs_n); assert_same(rew.cpu().numpy(), rew_n)
+        assert np.array_equal(done.cpu().numpy(), done_n) and np.array_equal(info["niter"].cpu().numpy(), info_n.niter)
+    seeds = env.seed(10)
+    assert len(seeds) == n and seeds[0] == 10 and seeds[n - 1] == 10 + n - 1
+    assert env.seed(None)[0] is None
+    env.step_async(act)
+    assert env.step_wait()[0].shape == (n, 2, 5)
+    assert len(env.get_attr("M")) == n and env.get_attr("restol", indices=[0, 5]) == [1e-10, 1e-10]
+    env.env_method("set_num_episodes", 7)
+    assert env.envs[3].num_episodes == 7
+    env.set_attr("num_episodes", 9, indices=[3])
+    assert env.envs[3].num_episodes == 9 and env.envs[4].num_episodes == 7
+    env.close()
