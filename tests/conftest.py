@@ -29,3 +29,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_artifacts():
+    """Fresh checkout: build libsdcgym.so (nvcc cross-compiles without a GPU) and the CPU oracle before any test."""
+    from sdc_gym_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        from sdc_gym_b200.build import build_library
+
+        build_library()
+    from oracle import exact
+
+    exact.build()
+    yield
