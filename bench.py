@@ -142,8 +142,10 @@ def run_reference(args):
         return
     import multiprocessing as mp
 
-    cores = os.cpu_count() or 1
     per_step = max(0.5, min(4.0, 150.0 / max(1, args.steps + args.warmup)))
+    if os.environ.get("SDCGYM_BENCH_REF_SECONDS"):  # tests shorten the samples
+        per_step = float(os.environ["SDCGYM_BENCH_REF_SECONDS"])
+    cores = int(os.environ.get("SDCGYM_BENCH_REF_CORES", os.cpu_count() or 1))
     ctx = mp.get_context("spawn")
     total_steps, total_time = 0, 0.0
     with ctx.Pool(cores) as pool:
