@@ -301,6 +301,10 @@ def run_ours(args):
                                         "MEASURED_PEAKS.json has no fp64 entry",
                          "algorithmic_flops_per_launch": alg_flops, "kernel_ms": kernel_ms,
                          "mean_niter": sum_niter_local / N,
+                         "note": "bit-exact emulation of the reference's rounding sequence needs 183 FP64 instructions "
+                                 "(mul/add/fma, <= 1 FMA each) per 210-flop sweep: instruction-level ceiling of the "
+                                 "algorithmic fraction = 210/(2*183) = 0.57, x 0.87 lane efficiency (envs of a warp stop "
+                                 "at different sweeps) = 0.49; FP64 pipe measured 73 % busy (profiles/)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_env_step": BYTES_PER_ENV_STEP_V0,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}},
