@@ -23,14 +23,31 @@ struct TrsmTiles {
     }
 };
 
-#define AR_(i, j) Ar[(i) + (j) * M]
-#define AI_(i, j) Ai[(i) + (j) * M]
-#define BR_(i, j) Br[(i) + (j) * M]
-#define BI_(i, j) Bi[(i) + (j) * M]
+// storage of the LU work matrix: registers (two arrays) or a strided side store (shared memory, element k of this
+// thread at base[k * stride]; static indices either way)
+template <int M>
+struct RegMatrix {
+    double re[M * M], im[M * M];
+    SDCGYM_HD double& R(int i, int j) { return re[i + j * M]; }
+    SDCGYM_HD double& I(int i, int j) { return im[i + j * M]; }
+};
+template <int M>
+struct StridedMatrix {
+    // volatile: every use is a load from the side store; a cached copy would be a register (and then a spill) again
+    volatile double* base;
+    int stride;
+    SDCGYM_HD volatile double& R(int i, int j) { return base[(2 * (i + j * M)) * stride]; }
+    SDCGYM_HD volatile double& I(int i, int j) { return base[(2 * (i + j * M) + 1) * stride]; }
+};
 
-// in: A = P (column-major, split re/im).  out: B = inverse (column-major).  A is destroyed (holds LU).
-template <int M, int V>
-SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (&Br)[M * M], double (&Bi)[M * M]) {
+#define AR_(i, j) A.R((i), (j))
+#define AI_(i, j) A.I((i), (j))
+
+// in: A = P (column-major, split re/im), destroyed (holds LU afterwards).  The inverse is produced one column at a
+// time (the two triangular solves of different columns are independent) and handed to store(row, col, re, im), so
+// only A and one column of B are live: M = 6, 7 still fit the register file this way.
+template <int M, int V, class Mat, class Store>
+SDCGYM_HD void cinv_exact_reg_cols(Mat& A, Store&& store) {
     int perm[M];
 #pragma unroll
     for (int i = 0; i < M; i++) perm[i] = i;
@@ -139,14 +156,7 @@ SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (
         }
     }
 
-    // ------------------------------- zgetrs: B = P I, then two ztrsm -------------------------------
-#pragma unroll
-    for (int i = 0; i < M; i++)
-#pragma unroll
-        for (int c = 0; c < M; c++) {
-            BR_(i, c) = (perm[i] == c) ? 1.0 : 0.0;
-            BI_(i, c) = 0.0;
-        }
+    // ------------------------------- zgetrs: B = P I, then two ztrsm, column by column -------------------------------
     using T = TrsmTiles<M>;
     double invr[M], invi[M];
 #pragma unroll
@@ -156,9 +166,15 @@ SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (
         invi[i] = d.im;
     }
 #pragma unroll
-    for (int upper = 0; upper < 2; upper++) {
+    for (int col = 0; col < M; col++) {
+        double bcr[M], bci[M];
 #pragma unroll
-        for (int col = 0; col < M; col++) {
+        for (int i = 0; i < M; i++) {
+            bcr[i] = (perm[i] == col) ? 1.0 : 0.0;
+            bci[i] = 0.0;
+        }
+#pragma unroll
+        for (int upper = 0; upper < 2; upper++) {
 #pragma unroll
             for (int oi = 0; oi < T::nrt; oi++) {
                 const int t = upper ? T::upper_visit(oi) : oi;
@@ -176,10 +192,10 @@ SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (
 #pragma unroll
                                 for (int pp = 0; pp < M; pp++) {
                                     if (pp >= p_lo && pp < p_hi) {
-                                        Srr = dfma(AR_(i, pp), BR_(pp, col), Srr);
-                                        Sii = dfma(AI_(i, pp), BI_(pp, col), Sii);
-                                        Sri = dfma(AR_(i, pp), BI_(pp, col), Sri);
-                                        Sir = dfma(AI_(i, pp), BR_(pp, col), Sir);
+                                        Srr = dfma(AR_(i, pp), bcr[pp], Srr);
+                                        Sii = dfma(AI_(i, pp), bci[pp], Sii);
+                                        Sri = dfma(AR_(i, pp), bci[pp], Sri);
+                                        Sir = dfma(AI_(i, pp), bcr[pp], Sir);
                                     }
                                 }
                                 vr = dsub(Srr, Sii);
@@ -189,15 +205,15 @@ SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (
 #pragma unroll
                                 for (int pp = 0; pp < M; pp++) {
                                     if (pp >= p_lo && pp < p_hi) {
-                                        re = dfma(BR_(pp, col), AR_(i, pp), -dfma(BI_(pp, col), AI_(i, pp), -re));
-                                        im = dfma(BR_(pp, col), AI_(i, pp), dfma(BI_(pp, col), AR_(i, pp), im));
+                                        re = dfma(bcr[pp], AR_(i, pp), -dfma(bci[pp], AI_(i, pp), -re));
+                                        im = dfma(bcr[pp], AI_(i, pp), dfma(bci[pp], AR_(i, pp), im));
                                     }
                                 }
                                 vr = re;
                                 vi = im;
                             }
-                            BR_(i, col) = dsub(BR_(i, col), vr);
-                            BI_(i, col) = dsub(BI_(i, col), vi);
+                            bcr[i] = dsub(bcr[i], vr);
+                            bci[i] = dsub(bci[i], vi);
                         }
                     }
                 }
@@ -206,29 +222,44 @@ SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (
                 for (int s = 0; s < 4; s++) {
                     if (s < rs) {
                         const int i = upper ? r0 + rs - 1 - s : r0 + s;
-                        cplx ccv{BR_(i, col), BI_(i, col)};
+                        cplx ccv{bcr[i], bci[i]};
                         if (upper) ccv = cmul_blas<V>(cplx{invr[i], invi[i]}, ccv);
-                        BR_(i, col) = ccv.re;
-                        BI_(i, col) = ccv.im;
+                        bcr[i] = ccv.re;
+                        bci[i] = ccv.im;
 #pragma unroll
                         for (int s2 = 1; s2 < 4; s2++) {
                             if (s2 > s && s2 < rs) {
                                 const int k = upper ? r0 + rs - 1 - s2 : r0 + s2;
                                 const cplx pr = cmul_blas<V>(ccv, cplx{AR_(k, i), AI_(k, i)});
-                                BR_(k, col) = dsub(BR_(k, col), pr.re);
-                                BI_(k, col) = dsub(BI_(k, col), pr.im);
+                                bcr[k] = dsub(bcr[k], pr.re);
+                                bci[k] = dsub(bci[k], pr.im);
                             }
                         }
                     }
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < M; i++) store(i, col, bcr[i], bci[i]);
     }
+}
+
+// convenience form: inverse into column-major arrays B
+template <int M, int V>
+SDCGYM_HD void cinv_exact_reg(double (&Ar)[M * M], double (&Ai)[M * M], double (&Br)[M * M], double (&Bi)[M * M]) {
+    RegMatrix<M> A;
+#pragma unroll
+    for (int k = 0; k < M * M; k++) {
+        A.re[k] = Ar[k];
+        A.im[k] = Ai[k];
+    }
+    cinv_exact_reg_cols<M, V>(A, [&](int i, int c, double re, double im) {
+        Br[i + c * M] = re;
+        Bi[i + c * M] = im;
+    });
 }
 
 #undef AR_
 #undef AI_
-#undef BR_
-#undef BI_
 
 }  // namespace sdcgym

@@ -17,7 +17,7 @@
 namespace sdcgym {
 
 constexpr int kBlock = 128;
-constexpr int kRegInvMaxM = 5;  // largest M whose exact inverse is computed in registers (exact_inv_reg.cuh)
+constexpr int kRegInvMaxM = 7;  // largest M whose exact inverse runs on register-resident LU factors (exact_inv_reg.cuh)
 
 template <int M>
 struct StepParams {
@@ -324,23 +324,36 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             }
         };
         if constexpr (M <= kRegInvMaxM) {
-            double Ar[M * M], Ai[M * M], Br[M * M], Bi[M * M];
+            RegMatrix<M> A;
 #pragma unroll
             for (int r = 0; r < M; r++)
 #pragma unroll
                 for (int c = 0; c < M; c++) {
                     const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
-                    Ar[r + c * M] = dsub((r == c) ? 1.0 : 0.0, zq.re);
-                    Ai[r + c * M] = dsub(0.0, zq.im);
+                    A.R(r, c) = dsub((r == c) ? 1.0 : 0.0, zq.re);
+                    A.I(r, c) = dsub(0.0, zq.im);
                 }
-            cinv_exact_reg<M, V>(Ar, Ai, Br, Bi);
+            // the inverse arrives column by column: only the LU factors and one column are live in registers
+            cinv_exact_reg_cols<M, V>(A, [&](int r, int c, double re, double im) {
+                Pr[(DENSE && !PS) ? r * M + c : 0] = re;
+                Pi[(DENSE && !PS) ? r * M + c : 0] = im;
+            });
+        } else if constexpr (HOLD == 8) {
+            // M = 8, 9: the LU work matrix does not fit the register file: it lives in the side store (shared memory,
+            // same per-thread slots that hold C afterwards), the code stays fully unrolled over static indices
+            StridedMatrix<M> A{side, side_stride};
 #pragma unroll
             for (int r = 0; r < M; r++)
 #pragma unroll
                 for (int c = 0; c < M; c++) {
-                    Pr[DENSE ? r * M + c : 0] = Br[r + c * M];
-                    Pi[DENSE ? r * M + c : 0] = Bi[r + c * M];
+                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    A.R(r, c) = dsub((r == c) ? 1.0 : 0.0, zq.re);
+                    A.I(r, c) = dsub(0.0, zq.im);
                 }
+            cinv_exact_reg_cols<M, V>(A, [&](int r, int c, double re, double im) {
+                Pr[(DENSE && !PS) ? r * M + c : 0] = re;
+                Pi[(DENSE && !PS) ? r * M + c : 0] = im;
+            });
         } else if constexpr (PS) {
             cplx* A = pside;                                // LU work matrix now, C later (same per-thread slots)
             cplx* B = pside + (size_t)M * M * pstride;      // the inverse stays here
@@ -374,6 +387,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
 
     // ---- system matrix (optionally register resident) ----
     // experimental residency (tuning only): 6 = Re(C) in shared memory and Im(C) re-derived
+    constexpr bool CS = (HOLD == 4 || HOLD == 8);  // C lives in the (double) side store
     constexpr int NCR = (HOLD >= 1 && HOLD <= 3) ? M * M : 1, NCI = (HOLD == 2) ? M * M : 1;
     double Cr[NCR], Ci[NCI];
     if (HOLD >= 1) {
@@ -384,9 +398,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 double q = p.Q[r * M + c];
                 const double crv = (r == c) ? dsub(1.0, dmul(zr, q)) : -dmul(zr, q);
                 if (HOLD <= 3) Cr[(HOLD >= 1 && HOLD <= 3) ? r * M + c : 0] = crv;
-                if (HOLD == 4) side[(M * M + r * M + c) * side_stride] = crv;
+                if (CS) side[(M * M + r * M + c) * side_stride] = crv;
                 if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
-                if (HOLD == 3 || HOLD == 4) side[(r * M + c) * side_stride] = -dmul(zi, q);
+                if (HOLD == 3 || CS) side[(r * M + c) * side_stride] = -dmul(zi, q);
                 if (HOLD == 5) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
                 if (HOLD == 6) side[(r * M + c) * side_stride] = crv;
             }
@@ -456,13 +470,13 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 double q = p.Q[m * M + c];
                 if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
                 else if (HOLD == 6) cr[c] = vside[(m * M + c) * side_stride];
-                else if (HOLD == 4) cr[c] = vside[(M * M + m * M + c) * side_stride];
+                else if (CS) cr[c] = vside[(M * M + m * M + c) * side_stride];
                 else if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
                 if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
                 else if (HOLD == 6) ci[c] = -dmul(zi_s, q);
                 else if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
-                else if (HOLD >= 3) ci[c] = vside[(m * M + c) * side_stride];
+                else if (HOLD == 3 || CS) ci[c] = vside[(m * M + c) * side_stride];
                 else ci[c] = -dmul(zi_s, q);
             }
             zgemv_rowdot<M, V>(cr, ci, ur, ui, yr, yi);
@@ -609,7 +623,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
 template <int M, int HOLD, int BLOCK = kBlock>
 constexpr size_t step_kernel_smem_bytes() {
     return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double)
-                     : (HOLD == 4 ? (size_t)2 * M * M * BLOCK * sizeof(double)
+                     : ((HOLD == 4 || HOLD == 8) ? (size_t)2 * M * M * BLOCK * sizeof(double)
                                   : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double)
                                                : (HOLD == 6 ? (size_t)M * M * BLOCK * sizeof(double) : 0)));
 }

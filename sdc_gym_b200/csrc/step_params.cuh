@@ -82,11 +82,12 @@ struct HoldPolicy {
     static constexpr int diag = (M <= 4) ? 1 : ((M <= 7) ? 4 : 0);  // M >= 8: 2 blocks of 64 threads lose to recomputing
     static constexpr int diag_minb = (M <= 5) ? 4 : 2;
     static constexpr int diag_block = 128;
-    // M >= 6: the M x M inverse no longer fits the register file.  Keeping inverse, Pinv and C in shared memory as
-    // complex pairs (HOLD 5, implemented and parity-tested) leaves room for only 2-4 warps per SM and measured
-    // 10-60 % slower than per-thread local memory at 8 warps/SM (profiles/README.md), so local memory it is.
-    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : 0);
-    static constexpr int dense_block = 128;
+    // dense kernels: M <= 5 keep the inverse in registers and C in shared memory (HOLD 4); M = 6, 7 run the inverse on
+    // register-resident LU factors and re-derive C (HOLD 0); M = 8, 9 keep the LU work matrix, then C, in shared
+    // memory (HOLD 8) in 64-thread blocks.  (Keeping Pinv in shared memory as well - HOLD 5, parity-tested - leaves
+    // only 2-4 warps per SM and measured slower than letting Pinv spill to local memory.)
+    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : ((M <= 7) ? 0 : 8));
+    static constexpr int dense_block = (M <= 7) ? 128 : 64;
     static constexpr int dense_minb = (M == 4 || M == 5) ? SDCGYM_DENSE_MINB : 2;
     static constexpr int step = 0;
     static constexpr int step_minb = (M <= 5) ? 6 : ((M <= 7) ? 3 : 2);  // M=5: 80 regs, 24 warps/SM: +12 % (profiles/tune_r01_v1.log)

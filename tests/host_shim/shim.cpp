@@ -124,8 +124,7 @@ static int step_m_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const 
 }
 extern "C" int shim_step_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
     switch (d->M) {
-    case 6: return step_m_hold5<6>(d, st, io);
-    case 7: return step_m_hold5<7>(d, st, io);
+    case 8: return step_m_hold5<8>(d, st, io);
     case 9: return step_m_hold5<9>(d, st, io);
     }
     return -2;

@@ -112,9 +112,9 @@ def test_philox_draws_curriculum_and_fused_autoreset_on_host():
 
 def test_shared_memory_formulation_of_large_dense_kernels():
     """HOLD 5 (inverse work matrix, Pinv and C in the complex side store): same bits as the oracle"""
-    _run("sdc-v0", 7, 200, prec_type="lower_tri", seed=21, entry="shim_step_hold5")
+    _run("sdc-v0", 8, 200, prec_type="lower_tri", seed=21, entry="shim_step_hold5")
     _run("sdc-v0", 9, 100, prec="LU", seed=22, entry="shim_step_hold5")
-    _run("sdc-v1", 6, 100, prec_type="strictly_lower_tri", steps=10, seed=23, entry="shim_step_hold5")
+    _run("sdc-v1", 8, 100, prec_type="strictly_lower_tri", steps=10, seed=23, entry="shim_step_hold5")
 
 
 def test_spectral_radius_gradient_against_eigenvector_formula_and_finite_differences():
