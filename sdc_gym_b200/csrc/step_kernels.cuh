@@ -338,7 +338,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 Pr[(DENSE && !PS) ? r * M + c : 0] = re;
                 Pi[(DENSE && !PS) ? r * M + c : 0] = im;
             });
-        } else if constexpr (HOLD == 8) {
+        } else if constexpr (HOLD == 8 || HOLD == 9) {
             // M = 8, 9: the LU work matrix does not fit the register file: it lives in the side store (shared memory,
             // same per-thread slots that hold C afterwards), the code stays fully unrolled over static indices
             StridedMatrix<M> A{side, side_stride};
@@ -385,12 +385,21 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         }
     }
 
+    if constexpr (HOLD == 9) {
+        // the LU work matrix is dead: its slots now hold Pinv (re at k, im at M^2 + k), read back in every sweep
+#pragma unroll
+        for (int k = 0; k < M * M; k++) {
+            side[k * side_stride] = Pr[DENSE ? k : 0];
+            side[(M * M + k) * side_stride] = Pi[DENSE ? k : 0];
+        }
+    }
+
     // ---- system matrix (optionally register resident) ----
     // experimental residency (tuning only): 6 = Re(C) in shared memory and Im(C) re-derived
     constexpr bool CS = (HOLD == 4 || HOLD == 8);  // C lives in the (double) side store
     constexpr int NCR = (HOLD >= 1 && HOLD <= 3) ? M * M : 1, NCI = (HOLD == 2) ? M * M : 1;
     double Cr[NCR], Ci[NCI];
-    if (HOLD >= 1) {
+    if (HOLD >= 1 && HOLD != 9) {
 #pragma unroll
         for (int r = 0; r < M; r++)
 #pragma unroll
@@ -435,7 +444,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         (void)vside;
         (void)vp;
 #ifdef __CUDA_ARCH__
-        if (HOLD < 2 || HOLD == 6) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
+        if (HOLD < 2 || HOLD == 6 || HOLD == 9) asm volatile("" : "+d"(zr_s), "+d"(zi_s));  // (HOLD 3 never uses zi_s)
 #endif
         double dr[M], di[M];
 #pragma unroll
@@ -449,6 +458,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                     if (PS) {
                         ar[c] = vp[(M * M + m + c * M) * pstride].re;  // B is column-major
                         ai[c] = vp[(M * M + m + c * M) * pstride].im;
+                    } else if (HOLD == 9) {
+                        ar[c] = vside[(m * M + c) * side_stride];
+                        ai[c] = vside[(M * M + m * M + c) * side_stride];
                     } else {
                         ar[c] = Pr[(DENSE && !PS) ? m * M + c : 0];
                         ai[c] = Pi[(DENSE && !PS) ? m * M + c : 0];
@@ -471,7 +483,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
                 else if (HOLD == 6) cr[c] = vside[(m * M + c) * side_stride];
                 else if (CS) cr[c] = vside[(M * M + m * M + c) * side_stride];
-                else if (HOLD >= 1) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
+                else if (HOLD >= 1 && HOLD != 9) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
                 if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
                 else if (HOLD == 6) ci[c] = -dmul(zi_s, q);
@@ -623,7 +635,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
 template <int M, int HOLD, int BLOCK = kBlock>
 constexpr size_t step_kernel_smem_bytes() {
     return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double)
-                     : ((HOLD == 4 || HOLD == 8) ? (size_t)2 * M * M * BLOCK * sizeof(double)
+                     : ((HOLD == 4 || HOLD == 8 || HOLD == 9) ? (size_t)2 * M * M * BLOCK * sizeof(double)
                                   : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double)
                                                : (HOLD == 6 ? (size_t)M * M * BLOCK * sizeof(double) : 0)));
 }

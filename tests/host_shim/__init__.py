@@ -44,6 +44,7 @@ def shim():
         L.shim_reset.argtypes = [ctypes.POINTER(_lib.EnvDesc), ctypes.POINTER(_lib.State), vp, vp, vp]
         L.shim_step.argtypes = [ctypes.POINTER(_lib.EnvDesc), ctypes.POINTER(_lib.State), ctypes.POINTER(_lib.StepIO)]
         L.shim_step_hold5.argtypes = L.shim_step.argtypes
+        L.shim_step_hold9.argtypes = L.shim_step.argtypes
         L.shim_spectral_radius.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64, vp, vp, vp]
         _shim = L
     return _shim

@@ -122,6 +122,26 @@ static int step_m_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const 
     }
     return -2;
 }
+template <int M>
+static int step_m_hold9(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    StepParams<M> p;
+    fill_params<M>(p, d, st);
+    fill_step_io<M>(p, io);
+    double side[3 * 2 * M * M];  // stride 3
+    for (int64_t i = 0; i < p.N; i++) {
+        if (d->env_kind == SDCGYM_ENV_FULL) step_one<M, 0, 0, true, 9>(p, i, side, 3);
+        else step_one<M, 1, 0, true, 9>(p, i, side, 3);
+    }
+    return 0;
+}
+extern "C" int shim_step_hold9(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
+    switch (d->M) {
+    case 8: return step_m_hold9<8>(d, st, io);
+    case 9: return step_m_hold9<9>(d, st, io);
+    }
+    return -2;
+}
+
 extern "C" int shim_step_hold5(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io) {
     switch (d->M) {
     case 8: return step_m_hold5<8>(d, st, io);

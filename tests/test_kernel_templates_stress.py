@@ -178,3 +178,10 @@ def test_even_M_on_host(M):
     _run("sdc-v0", M, 200, prec="LU", seed=71 + M)
     _run("sdc-v0", M, 200, prec_type="lower_tri", seed=72 + M)
     _run("sdc-v1", M, 100, mode="uniform", steps=12, strategy="residual_change", seed=73 + M)
+
+
+def test_pinv_in_side_store_formulation():
+    """HOLD 9 (M = 8, 9 dense): LU work matrix, then Pinv, in the side store; C re-derived"""
+    _run("sdc-v0", 9, 150, prec_type="lower_tri", seed=31, entry="shim_step_hold9")
+    _run("sdc-v0", 8, 150, prec="LU", seed=32, entry="shim_step_hold9")
+    _run("sdc-v1", 9, 80, prec_type="strictly_lower_tri", steps=10, seed=33, entry="shim_step_hold9")
