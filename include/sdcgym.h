@@ -182,10 +182,12 @@ int sdcgym_spectral_radius_grad(const sdcgym_rho_desc* desc, int64_t N, const do
  * r' = u0 - C u', norm = ||r'||_inf.  lam [N], u0/u/r_old/u_out/r_out [N][M] complex128 interleaved,
  * qd as in sdcgym_spectral_radius, Cs [N][M][M] complex128 or NULL (then C = I - lam*dt*Q is formed on the fly).
  * JAX arithmetic in the reference: agreement is to rounding level (1e-12 relative), not bit-exact.
+ * grad (optional, [N][A][2]): d norm / d theta_k as complex g with d norm = Re(sum_k g_k d theta_k) - the
+ * per-sample gradient jax.value_and_grad(loss) needs for the residual loss (dp_playground.py:1073).
  */
 int sdcgym_residual_step(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, const double* Cs,
                          const double* u0, const double* u, const double* r_old, double* u_out, double* r_out,
-                         double* norm_out, void* stream);
+                         double* norm_out, double* grad, void* stream);
 
 /*
  * Device-side VecNormalize building blocks (SB3 RunningMeanStd semantics; utils/utils.py:295-312).

@@ -168,7 +168,7 @@ def load():
     L.sdcgym_spectral_radius_grad.argtypes = [ctypes.POINTER(RhoDesc), i64, vp, vp, vp, vp, vp]
     L.sdcgym_spectral_radius_grad.restype = ctypes.c_int
     dp_ = ctypes.POINTER(RhoDesc)
-    L.sdcgym_residual_step.argtypes = [dp_, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sdcgym_residual_step.argtypes = [dp_, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_scratch_doubles.argtypes = [ctypes.c_int]
     L.sdcgym_vecnorm_accumulate.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_merge.argtypes = [ctypes.c_int, dbl, vp, vp, vp, vp, vp]

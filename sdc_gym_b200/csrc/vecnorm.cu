@@ -121,6 +121,7 @@ struct ResParams {
     int64_t N;
     const double *lam, *qd, *Cs, *u0, *u, *r_old;
     double *u_out, *r_out, *norm_out;
+    double* grad;  // optional [N][A][2]: d ||r'||inf / d theta_k as complex g (d = Re(sum g_k d theta_k))
     double dt;
     int32_t prec_type, qd_is_complex, n_act;
 };
@@ -167,6 +168,8 @@ __global__ void __launch_bounds__(128) residual_step_kernel(const __grid_constan
     }
     double nrm = 0.0;
     bool nan = false;
+    int kmax = 0;
+    C2 rk{0.0, 0.0};
 #pragma unroll
     for (int r = 0; r < M; r++) {
         C2 acc{0.0, 0.0};
@@ -184,22 +187,68 @@ __global__ void __launch_bounds__(128) residual_step_kernel(const __grid_constan
         p.r_out[(i * M + r) * 2 + 1] = res.i;
         double a = hypot(res.r, res.i);
         nan |= isnan(a);
-        nrm = a > nrm ? a : nrm;
+        if (a > nrm) {
+            nrm = a;
+            kmax = r;
+            rk = res;
+        }
     }
     p.norm_out[i] = nan ? CUDART_NAN : nrm;
+    if (p.grad) {
+        // d r' = -z C P^{-1} dQd delta  =>  d ||r'||inf = Re( conj(r'_k)/|r'_k| * (-z) a_i delta_j dQd_ij ),
+        // a = P^{-T} C_{k,:}^T (back substitution on the upper-triangular P^T), k = argmax |r'_m|
+        C2 a[M];
+#pragma unroll
+        for (int m = M - 1; m >= 0; m--) {
+            C2 ck{0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < M; r++)
+                if (r == kmax) {
+                    if (p.Cs) ck = C2{p.Cs[((i * M + r) * M + m) * 2], p.Cs[((i * M + r) * M + m) * 2 + 1]};
+                    else ck = C2{(r == m ? 1.0 : 0.0) - z.r * p.Q[r * M + m], -z.i * p.Q[r * M + m]};
+                }
+            C2 acc = ck;
+#pragma unroll
+            for (int q = m + 1; q < M; q++) acc = c_add(acc, c_mul(c_mul(z, Qd[q * M + m]), a[q]));  // - P_qm a_q
+            a[m] = c_div(acc, c_sub(C2{1.0, 0.0}, c_mul(z, Qd[m * M + m])));
+        }
+        C2 f{0.0, 0.0};
+        if (nrm > 0.0 && !nan) f = c_mul(c_scale(c_conj(rk), 1.0 / nrm), C2{-z.r, -z.i});
+        double* g = p.grad + i * (int64_t)p.n_act * 2;
+        int kk = 0;
+#pragma unroll
+        for (int r = 0; r < M; r++)
+#pragma unroll
+            for (int c = 0; c < M; c++) {
+                bool take = false;
+                switch (p.prec_type) {
+                case SDCGYM_PREC_DIAG: take = (c == r); break;
+                case SDCGYM_PREC_LOWER_DIAG: take = (r == c + 1); break;
+                case SDCGYM_PREC_LOWER_TRI: take = (c <= r); break;
+                case SDCGYM_PREC_STRICTLY_LOWER_TRI: take = (c < r); break;
+                default: break;
+                }
+                if (take) {
+                    const C2 gv = c_mul(f, c_mul(a[r], dl[c]));
+                    g[2 * kk] = gv.r;
+                    g[2 * kk + 1] = gv.i;
+                    kk++;
+                }
+            }
+    }
 }
 
 template <int M>
 static int launch_residual(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd, const double* Cs,
                            const double* u0, const double* u, const double* r_old, double* u_out, double* r_out,
-                           double* norm_out, cudaStream_t s) {
+                           double* norm_out, double* grad, cudaStream_t s) {
     ResParams<M> p;
     for (int k = 0; k < M * M; k++) {
         p.Q[k] = d->Q[k];
         p.Qd[k] = d->Qd_fixed[k];
     }
     p.N = N; p.lam = lam; p.qd = qd; p.Cs = Cs; p.u0 = u0; p.u = u; p.r_old = r_old;
-    p.u_out = u_out; p.r_out = r_out; p.norm_out = norm_out;
+    p.u_out = u_out; p.r_out = r_out; p.norm_out = norm_out; p.grad = grad;
     p.dt = d->dt; p.prec_type = d->prec_type; p.qd_is_complex = d->qd_is_complex;
     p.n_act = sdcgym_num_actions(M, d->prec_type);
     residual_step_kernel<M><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(p);
@@ -300,16 +349,17 @@ extern "C" int sdcgym_vecnorm_reward(int64_t N, const double* reward, const uint
 
 extern "C" int sdcgym_residual_step(const sdcgym_rho_desc* d, int64_t N, const double* lam, const double* qd,
                                     const double* Cs, const double* u0, const double* u, const double* r_old,
-                                    double* u_out, double* r_out, double* norm_out, void* stream) {
+                                    double* u_out, double* r_out, double* norm_out, double* grad, void* stream) {
     if (!d) return SDCGYM_ENULL;
     if (!sdcgym_supported(d->M, d->prec_type)) return SDCGYM_EUNSUPPORTED;
     if (N < 0) return SDCGYM_EINVAL;
     if (N == 0) return 0;
     if (!lam || !u0 || !u || !r_old || !u_out || !r_out || !norm_out) return SDCGYM_ENULL;
     if (d->prec_type != SDCGYM_PREC_FIXED && !qd) return SDCGYM_ENULL;
+    if (grad && d->prec_type == SDCGYM_PREC_FIXED) return SDCGYM_EUNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     switch (d->M) {
-#define C(m) case m: return launch_residual<m>(d, N, lam, qd, Cs, u0, u, r_old, u_out, r_out, norm_out, s);
+#define C(m) case m: return launch_residual<m>(d, N, lam, qd, Cs, u0, u, r_old, u_out, r_out, norm_out, grad, s);
         C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)
 #undef C
     }

@@ -219,12 +219,13 @@ class ResidualLoss:
         t = t.to(self.device).to(torch.complex128).reshape(shape).contiguous()
         return torch.view_as_real(t)
 
-    def take_step(self, lams, outputs, Cs, u0s, us, old_residuals):
+    def take_step(self, lams, outputs, Cs, u0s, us, old_residuals, with_grad=False):
         torch = _torch()
         sr, M = self._sr, self.M
         lam = self._c128(lams, (-1,))
         B = lam.shape[0]
-        qd, is_c, bc = sr._outputs_tensor(outputs, B)
+        out = outputs.detach() if isinstance(outputs, torch.Tensor) else outputs
+        qd, is_c, bc = sr._outputs_tensor(out, B)
         if bc:
             qd = qd.expand(B, *qd.shape[1:]).contiguous()
         d = sr._desc
@@ -234,13 +235,31 @@ class ResidualLoss:
         u_out = torch.empty((B, M, 2), dtype=torch.float64, device=self.device)
         r_out = torch.empty((B, M, 2), dtype=torch.float64, device=self.device)
         norms = torch.empty(B, dtype=torch.float64, device=self.device)
+        grad = torch.empty((B, sr.n_out, 2), dtype=torch.float64, device=self.device) if with_grad else None
         _lib.check(sr._L.sdcgym_residual_step(
             ctypes.byref(d), B, lam.data_ptr(), None if qd is None else qd.data_ptr(),
             None if C is None else C.data_ptr(), u0.data_ptr(), u.data_ptr(), r.data_ptr(), u_out.data_ptr(),
-            r_out.data_ptr(), norms.data_ptr(), sr._stream()), "sdcgym_residual_step")
+            r_out.data_ptr(), norms.data_ptr(), None if grad is None else grad.data_ptr(), sr._stream()),
+            "sdcgym_residual_step")
         self._keep = (lam, qd, C, u0, u, r)
-        return torch.view_as_complex(u_out), torch.view_as_complex(r_out), norms
+        res = (torch.view_as_complex(u_out), torch.view_as_complex(r_out), norms)
+        return res + (torch.view_as_complex(grad),) if with_grad else res
 
     def __call__(self, lams, outputs, Cs, u0s, us, old_residuals):
         us_new, residuals, norms = self.take_step(lams, outputs, Cs, u0s, us, old_residuals)
         return self._sr.mean(norms), us_new, residuals
+
+    def value_and_grad(self, lams, outputs, Cs, u0s, us, old_residuals, convention="jax"):
+        """((loss, us', residuals'), d loss / d outputs): ``jax.value_and_grad(loss, has_aux=True)`` for the residual
+        loss (``dp_playground.py:1038-1073``); gradient conventions as in ``SpectralRadiusLoss.value_and_grad``."""
+        torch = _torch()
+        us_new, residuals, norms, g = self.take_step(lams, outputs, Cs, u0s, us, old_residuals, with_grad=True)
+        g = g / norms.numel()
+        is_c = (outputs.is_complex() if isinstance(outputs, torch.Tensor) else np.iscomplexobj(outputs))
+        if not is_c:
+            g = g.real
+        elif convention == "torch":
+            g = g.conj()
+        elif convention != "jax":
+            raise ValueError("convention must be 'jax' or 'torch'")
+        return (self._sr.mean(norms), us_new, residuals), g

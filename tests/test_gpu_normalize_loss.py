@@ -254,3 +254,30 @@ def test_examples_reproduce_reference_baseline_numbers_and_train():
     tr = load("train_diag_spectral_radius")
     hist, theta = tr.main(["--steps", "120", "--batch", "16384"])
     assert hist[-1] < 0.6 * hist[0] and np.all(theta > 0) and np.all(theta < 1)
+
+
+@pytest.mark.parametrize("prec_type", ["diag", "lower_tri"])
+def test_residual_loss_gradient_against_finite_differences(prec_type):
+    from sdc_gym_b200.loss import ResidualLoss
+    M, B = 5, 512
+    rng = np.random.default_rng(4)
+    A = num_actions(M, prec_type)
+    lam = rng.uniform(-100, 0, B) + 1j * rng.uniform(-10, 0, B)
+    out = rng.uniform(0.05, 0.3, (B, A)) + 1j * rng.uniform(-0.05, 0.05, (B, A))
+    u0 = rng.uniform(0, 1, (B, M)) + 1j * rng.uniform(0, 1, (B, M))
+    u = rng.uniform(0, 1, (B, M)) + 1j * rng.uniform(0, 1, (B, M))
+    Q = collocation_matrix(M)
+    res = u0 - np.einsum("bij,bj->bi", np.eye(M)[None] - lam[:, None, None] * Q[None], u)
+    loss = ResidualLoss(M, 1.0, prec_type)
+    (val, u_new, r_new), g = loss.value_and_grad(lam, out, None, u0, u, res)
+    val0, _, _ = loss(lam, out, None, u0, u, res)
+    assert abs(float(val) - float(val0)) <= 1e-14 * float(val0)
+    g = g.cpu().numpy()
+    dirv = rng.normal(size=(B, A)) + 1j * rng.normal(size=(B, A))
+    h = 1e-7
+    fp = float(loss(lam, out + h * dirv, None, u0, u, res)[0])
+    fm = float(loss(lam, out - h * dirv, None, u0, u, res)[0])
+    an = np.real(np.sum(g * dirv))
+    assert abs((fp - fm) / (2 * h) - an) <= 1e-5 * abs(an), ((fp - fm) / (2 * h), an)
+    (_, _, _), g_r = loss.value_and_grad(lam, out.real.copy(), None, u0, u, res)
+    assert not g_r.is_complex() and g_r.shape == (B, A)
