@@ -135,6 +135,26 @@ def cpu_baseline_single(seconds=10.0):
                       f"reference env (oracle/sdc_port.py)"}
 
 
+def cpu_c_oracle_single(envs=16384):
+    """Extra context: the plain-C rounding-exact restatement (oracle/sdc_exact.c) on one core - an upper bound for
+    what a compiled CPU implementation of the same arithmetic does; the reference itself is the numpy figure."""
+    import numpy as np
+    from oracle import exact
+    from sdc_gym_b200.collocation import collocation_matrix
+
+    rng = np.random.default_rng(0)
+    Q = collocation_matrix(M)
+    lam = rng.uniform(-100, 0, envs) + 1j * rng.uniform(-10, 0, envs)
+    act = rng.uniform(-1, 1, (envs, M))
+    u, r = exact.reset(Q, 1.0, lam)
+    niter = np.zeros(envs, np.int32)
+    t0 = time.perf_counter()
+    exact.step("sdc-v0", Q, 1.0, lam, u, r, niter, r.copy(), act)
+    el = time.perf_counter() - t0
+    return {"value": envs / el, "unit": UNIT, "cores": 1, "kind": "port (plain C, rounding-exact oracle)",
+            "sample": f"{envs} sdc-v0 env-steps in {el:.2f} s, mean niter {niter.mean():.1f}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (numpy port, see oracle/sdc_port.py) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -278,9 +298,10 @@ def run_ours(args):
     h2d = N * M * 8
     d2h = N * (2 * M * 16 + 8 + 1 + 4 + 8 + 16)
 
-    cpu = None
+    cpu, cpu_c = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_single(args.cpu_seconds)
+        cpu_c = cpu_c_oracle_single()
 
     if rank == 0:
         line = {
@@ -313,6 +334,7 @@ def run_ours(args):
                     "api": "SDCVecEnv.step(numpy actions in pinned memory) -> numpy obs, rewards, dones, infos "
                            "(terminal observations stay on the device until an info dict asks for them)"},
             "cpu_baseline": cpu,
+            "cpu_baseline_c_oracle": cpu_c,
             "clocks": clocks,
             "rollout_stats": {"sum_reward": float(stats[0]), "sum_niter": float(stats[1]),
                               "converged": float(stats[2]), "diverged": float(stats[3]),
