@@ -74,6 +74,9 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
 //  * M <= 4: C is small enough to stay in registers.
 //  * dense kernels spend their registers on the M x M inverse; sdc-v1 runs one sweep per launch and is memory
 //    bound: nothing is held, occupancy is maximised.
+#ifndef SDCGYM_DENSE_MID
+#define SDCGYM_DENSE_MID 9  // residency of the M = 6, 7 dense kernels (0 or 9)
+#endif
 #ifndef SDCGYM_DENSE_BIG
 #define SDCGYM_DENSE_BIG 9  // residency of the M = 8, 9 dense kernels (8 or 9, see step_kernels.cuh)
 #endif
@@ -89,7 +92,7 @@ struct HoldPolicy {
     // register-resident LU factors and re-derive C (HOLD 0); M = 8, 9 keep the LU work matrix, then Pinv, in shared
     // memory and re-derive C (HOLD 9; HOLD 8 = C instead of Pinv there measured 25 % slower) in 64-thread blocks.  (Keeping Pinv in shared memory as well - HOLD 5, parity-tested - leaves
     // only 2-4 warps per SM and measured slower than letting Pinv spill to local memory.)
-    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : ((M <= 7) ? 0 : SDCGYM_DENSE_BIG));
+    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : ((M <= 7) ? SDCGYM_DENSE_MID : SDCGYM_DENSE_BIG));
     static constexpr int dense_block = (M <= 7) ? 128 : 64;
     static constexpr int dense_minb = (M == 4 || M == 5) ? SDCGYM_DENSE_MINB : 2;
     static constexpr int step = 0;
