@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "step_params.cuh"
+#include "team_kernels.cuh"
 
 #ifndef SDCGYM_M
 #error "compile with -DSDCGYM_M=<2..9>"
@@ -29,8 +30,8 @@ static int tune_variant() {
 
 template <int KIND, int V, bool DENSE>
 static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
-    const unsigned grid = (unsigned)((p.N + kBlock - 1) / kBlock);
 #ifdef SDCGYM_TUNE_VARIANTS
+    const unsigned grid = (unsigned)((p.N + kBlock - 1) / kBlock);
     if constexpr (kM == 5 && KIND == SDCGYM_ENV_FULL && !DENSE && V == 0) {
         switch (tune_variant()) {
         case 1: step_kernel<kM, KIND, V, DENSE, 2, 2><<<grid, kBlock, 0, s>>>(p); return cudaGetLastError();
@@ -103,6 +104,21 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         }
     }
 #endif
+    if constexpr (DENSE && kM >= kTeamMinM) {
+        // large dense Q_delta: one env per team of M lanes (team_kernels.cuh); collect_states keeps the per-thread kernel
+        static const bool no_team = getenv("SDCGYM_NO_TEAM") != nullptr;  // A/B switch for tools/bench_dense.py
+        if (p.old_states == nullptr && !no_team) {
+            constexpr int envs_per_block = (kTeamBlock / 32) * (32 / kM);
+#ifdef SDCGYM_TUNE_VARIANTS
+            static const int tt = getenv("SDCGYM_TEAM_TUNE") ? atoi(getenv("SDCGYM_TEAM_TUNE")) : 0;
+            if (tt == 2) { team_step_kernel<kM, KIND, V, 2><<<(unsigned)((p.N + envs_per_block - 1) / envs_per_block), kTeamBlock, 0, s>>>(p); return cudaGetLastError(); }
+            if (tt == 4) { team_step_kernel<kM, KIND, V, 4><<<(unsigned)((p.N + envs_per_block - 1) / envs_per_block), kTeamBlock, 0, s>>>(p); return cudaGetLastError(); }
+            if (tt == 5) { team_step_kernel<kM, KIND, V, 5><<<(unsigned)((p.N + envs_per_block - 1) / envs_per_block), kTeamBlock, 0, s>>>(p); return cudaGetLastError(); }
+#endif
+            team_step_kernel<kM, KIND, V><<<(unsigned)((p.N + envs_per_block - 1) / envs_per_block), kTeamBlock, 0, s>>>(p);
+            return cudaGetLastError();
+        }
+    }
     constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
     constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);
