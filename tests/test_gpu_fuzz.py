@@ -1,0 +1,94 @@
+"""GPU: seeded random configurations of the env constructor (sdc_env.py:38-104 arguments) through the CUDA path against
+the rounding-exact oracle.  Each case draws M, env kind, preconditioner family, dt, restol, reward strategy and its
+weights, the BLAS variant and the lambda box (boxes that reach into the right half plane exercise divergence / the
+error penalty), then compares a short rollout: states and residual norms bit for bit, iteration counts and flags
+exactly, rewards to 1e-14 relative."""
+import numpy as np
+import pytest
+
+import sdc_gym_b200
+from oracle import exact
+from sdc_gym_b200 import _lib
+from sdc_gym_b200.collocation import collocation_matrix
+from sdc_gym_b200.precond import fixed_preconditioner, num_actions
+from tests.helpers import assert_reward_close, assert_same
+
+pytestmark = pytest.mark.gpu
+
+STRATEGIES = ["iteration_only", "residual_change", "gauss_kernel", "fast_convergence", "smooth_fast_convergence",
+              "smoother_fast_convergence"]
+FAMILIES = [("diag", None, False), ("diag", None, True), ("lower_diag", None, False), ("lower_tri", None, False),
+            ("strictly_lower_tri", None, True), ("lower_tri", None, True), ("diag", "LU", False), ("diag", "EE", False),
+            ("diag", "min", False), ("diag", "zeros", False)]
+
+
+def draw_case(seed):
+    g = np.random.default_rng(1000 + seed)
+    prec_type, prec, cplx = FAMILIES[g.integers(len(FAMILIES))]
+    M = int(g.integers(2, 10))
+    if prec == "min" and M not in (3, 5, 7):
+        prec = "LU"
+    re_hi = float(g.choice([0.0, 0.0, 0.5, 2.0]))
+    return dict(
+        kind=str(g.choice(["sdc-v0", "sdc-v1"])), M=M, prec_type=prec_type, prec=prec, cplx=cplx,
+        dt=float(g.choice([0.05, 0.5, 1.0, 1.0, 3.0])), restol=float(g.choice([1e-4, 1e-8, 1e-10, 1e-13, 1e-300])),
+        strategy=str(g.choice(STRATEGIES)), step_penalty=float(g.choice([0.1, 0.03, 1.0])),
+        residual_weight=float(g.choice([0.5, 2.0])), norm_factor=float(g.choice([1.0, 1.0, 0.25, 7.0])),
+        variant=int(g.integers(2)), re=(float(g.choice([-100.0, -5.0, -1000.0])), re_hi),
+        im=(float(g.choice([-10.0, 0.0, -50.0])), float(g.choice([0.0, 10.0]))),
+        do_scale=bool(g.integers(2)), n=int(g.choice([257, 1000, 2049])), seed=int(seed))
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_configuration_equals_oracle(seed):
+    c = draw_case(seed)
+    g = np.random.default_rng(c["seed"])
+    n, M = c["n"], c["M"]
+    Q = collocation_matrix(M)
+    lam = g.uniform(c["re"][0], c["re"][1], n) + 1j * g.uniform(c["im"][0], c["im"][1], n)
+    fixed = c["prec"] is not None
+    do_scale = c["do_scale"] and c["prec_type"] == "diag" and not c["cplx"] and not fixed
+    env = sdc_gym_b200.make(c["kind"], num_envs=n, M=M, dt=c["dt"], restol=c["restol"], prec=c["prec"],
+                            prec_type=c["prec_type"], free_action_space=c["cplx"], do_scale=do_scale,
+                            reward_iteration_only=None, reward_strategy=c["strategy"], step_penalty=c["step_penalty"],
+                            residual_weight=c["residual_weight"], norm_factor=c["norm_factor"],
+                            blas_variant=_lib.BLAS_HASWELL if c["variant"] else _lib.BLAS_SKYLAKEX, autoreset=False,
+                            lambda_real_interval=list(c["re"]), lambda_imag_interval=list(c["im"]))
+    obs = env.reset(lam=lam)
+    u, r = exact.reset(Q, c["dt"], lam, variant=c["variant"])
+    assert_same(obs[:, 0], u, f"{c} reset u"); assert_same(obs[:, 1], r, f"{c} reset r")
+    rinit, niter = r.copy(), np.zeros(n, np.int32)
+    Qd = fixed_preconditioner(c["prec"], M, Q) if fixed else None
+    A = num_actions(M, c["prec_type"])
+    alive = np.ones(n, bool)
+    steps = 1 if c["kind"] == "sdc-v0" else 12
+    for s in range(steps):
+        if fixed:
+            act = None
+        elif c["cplx"]:
+            act = g.uniform(0, 0.5, (n, A)) + 1j * g.uniform(-0.1, 0.1, (n, A))
+        elif do_scale:
+            act = g.uniform(-1.2, 1.2, (n, A))  # beyond [-1, 1]: the clip of _scale_action is exercised
+        else:
+            act = g.uniform(0, 0.7, (n, A))
+        obs, rew, done, infos = env.step(act if act is not None else np.zeros((n, M)))
+        out = exact.step(c["kind"], Q, c["dt"], lam, u, r, niter, rinit, act,
+                         prec_type="fixed" if fixed else c["prec_type"], Qd_fixed=Qd, do_scale=do_scale,
+                         reward_strategy=c["strategy"], step_penalty=c["step_penalty"],
+                         residual_weight=c["residual_weight"], norm_factor=c["norm_factor"], restol=c["restol"],
+                         variant=c["variant"])
+        snap = env._snapshot()
+        what = f"{c} step {s}"
+        assert_same(snap["obs"][alive, 0], u[alive], what + " u")
+        assert_same(snap["obs"][alive, 1], r[alive], what + " r")
+        assert np.array_equal(infos.niter[alive], niter[alive]), what + " niter"
+        assert_same(infos.residual[alive], out["resnorm"][alive], what + " residual")
+        assert_reward_close(rew[alive], out["reward"][alive], what)
+        f = infos.flags
+        assert np.array_equal(((f & 4) != 0)[alive], out["err"][alive]), what + " err"
+        if c["kind"] == "sdc-v1":
+            assert np.array_equal(done[alive], out["done"][alive]), what + " done"
+            alive &= ~out["done"]
+        else:
+            assert np.array_equal(((f & 2) != 0)[alive], out["done"][alive]), what + " converged"
+            assert done.all()
