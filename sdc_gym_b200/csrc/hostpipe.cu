@@ -7,6 +7,7 @@
 // streams and events.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <new>
 
 #include "../../include/sdcgym.h"
@@ -14,7 +15,7 @@
 struct sdcgym_pipe {
     int device;
     int max_chunks;
-    cudaStream_t s_in, s_k, s_out;
+    cudaStream_t s_in, s_k, s_out, s_out2;  // s_out: observations, s_out2: the small per-env result arrays
     cudaEvent_t* ev_in;   // [max_chunks] actions of chunk c are on the device
     cudaEvent_t* ev_k;    // [max_chunks] kernels of chunk c are done
     cudaEvent_t ev_start;
@@ -39,6 +40,7 @@ extern "C" int sdcgym_pipe_create(int max_chunks, sdcgym_pipe** out) {
     PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
     PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_k, cudaStreamNonBlocking));
     PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    PIPE_CHECK(cudaStreamCreateWithFlags(&p->s_out2, cudaStreamNonBlocking));
     PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
     for (int c = 0; c < max_chunks; c++) {
         PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_in[c], cudaEventDisableTiming));
@@ -53,6 +55,7 @@ extern "C" int sdcgym_pipe_destroy(sdcgym_pipe* p) {
     cudaStreamSynchronize(p->s_in);
     cudaStreamSynchronize(p->s_k);
     cudaStreamSynchronize(p->s_out);
+    cudaStreamSynchronize(p->s_out2);
     for (int c = 0; c < p->max_chunks; c++) {
         cudaEventDestroy(p->ev_in[c]);
         cudaEventDestroy(p->ev_k[c]);
@@ -61,6 +64,7 @@ extern "C" int sdcgym_pipe_destroy(sdcgym_pipe* p) {
     cudaStreamDestroy(p->s_in);
     cudaStreamDestroy(p->s_k);
     cudaStreamDestroy(p->s_out);
+    cudaStreamDestroy(p->s_out2);
     delete[] p->ev_in;
     delete[] p->ev_k;
     delete p;
@@ -72,6 +76,13 @@ extern "C" int sdcgym_host_alloc(size_t bytes, void** out) {
     return (int)cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
 }
 extern "C" int sdcgym_host_free(void* p) { return p ? (int)cudaFreeHost(p) : 0; }
+
+static int64_t chunk_begin(int64_t N, int c, int chunks) {
+    if (c <= 0) return 0;
+    if (c >= chunks) return N;
+    const double f = (double)c / (double)chunks;
+    return (int64_t)((double)N * f * sqrt(f)) / 32 * 32;
+}
 
 extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st,
                                 const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host, int chunks,
@@ -92,10 +103,17 @@ extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, con
     PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_start, 0));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_out2, p->ev_start, 0));
+    // The observations are 80 % of the result bytes and go out chunk by chunk; the five small arrays (37 B/env) are
+    // copied once per group of chunks: fewer, larger DMA transfers (each copy costs a few microseconds of set-up).
+    const int group = chunks >= 4 ? chunks / 2 : 1;
+    int64_t small_lo = 0;
 
     double* act_dev = const_cast<double*>(dev->action);
     for (int c = 0; c < chunks; c++) {
-        int64_t lo = (N * c / chunks) / 32 * 32, hi = (c + 1 == chunks) ? N : (N * (c + 1) / chunks) / 32 * 32;
+        // chunk boundaries grow like c^1.5: a small first chunk starts the D2H stream (the bottleneck) early, the
+        // later, larger chunks keep the number of transfers low
+        const int64_t lo = chunk_begin(N, c, chunks), hi = chunk_begin(N, c + 1, chunks);
         if (hi <= lo) continue;
         const int64_t n = hi - lo;
         if (A > 0) {
@@ -128,19 +146,26 @@ extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, con
         }
         PIPE_CHECK(cudaEventRecord(p->ev_k[c], p->s_k));
         PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[c], 0));
-#define D2H(hostp, devp, bytes_per_env)                                                                             \
+#define D2H(strm, from, count, hostp, devp, bytes_per_env)                                                           \
     if ((hostp) && (devp))                                                                                          \
-        PIPE_CHECK(cudaMemcpyAsync((char*)(hostp) + (size_t)lo * (bytes_per_env), (const char*)(devp) + (size_t)lo * (bytes_per_env), \
-                                   (size_t)n * (bytes_per_env), cudaMemcpyDeviceToHost, p->s_out));
-        D2H(host->obs, obs_dev, 4 * M * sizeof(double))
-        D2H(host->reward, dev->reward, sizeof(double))
-        D2H(host->flags, dev->flags, 1)
-        D2H(host->niter, dev->info_niter, sizeof(int32_t))
-        D2H(host->residual, dev->info_residual, sizeof(double))
-        D2H(host->lam, dev->info_lam, 2 * sizeof(double))
+        PIPE_CHECK(cudaMemcpyAsync((char*)(hostp) + (size_t)(from) * (bytes_per_env),                                \
+                                   (const char*)(devp) + (size_t)(from) * (bytes_per_env),                          \
+                                   (size_t)(count) * (bytes_per_env), cudaMemcpyDeviceToHost, strm));
+        D2H(p->s_out, lo, n, host->obs, obs_dev, 4 * M * sizeof(double))
+        if ((c + 1) % group == 0 || c + 1 == chunks) {
+            PIPE_CHECK(cudaStreamWaitEvent(p->s_out2, p->ev_k[c], 0));
+            const int64_t sn = hi - small_lo;
+            D2H(p->s_out2, small_lo, sn, host->reward, dev->reward, sizeof(double))
+            D2H(p->s_out2, small_lo, sn, host->flags, dev->flags, 1)
+            D2H(p->s_out2, small_lo, sn, host->niter, dev->info_niter, sizeof(int32_t))
+            D2H(p->s_out2, small_lo, sn, host->residual, dev->info_residual, sizeof(double))
+            D2H(p->s_out2, small_lo, sn, host->lam, dev->info_lam, 2 * sizeof(double))
+            small_lo = hi;
+        }
 #undef D2H
     }
     PIPE_CHECK(cudaStreamSynchronize(p->s_out));
+    PIPE_CHECK(cudaStreamSynchronize(p->s_out2));
     // later work on the caller's stream must see the new state
     PIPE_CHECK(cudaEventRecord(p->ev_start, p->s_k));
     PIPE_CHECK(cudaStreamWaitEvent(cs, p->ev_start, 0));
