@@ -224,10 +224,12 @@ int sdcgym_gae(int T, int64_t N, const double* rewards, const double* values, co
 /*
  * Host-buffer step: `DummyVecEnv.step(actions)` with numpy-style HOST arrays on both sides, as one call.
  * Device buffers (state, staging for actions `dev->action` [N][A], outputs in `dev`, `obs_dev` [N][2][M] complex128)
- * stay caller-owned; the pipe owns three streams and its events.  The batch is cut into `chunks` pieces and
- * H2D(actions) | step + export kernels | D2H(results) are overlapped; the call returns when the host arrays are
- * filled.  Page-locked host memory (sdcgym_host_alloc, cudaHostAlloc, torch pin_memory) makes the copies
- * asynchronous; pageable memory works but serialises them.  NULL host outputs are skipped.
+ * stay caller-owned; the pipe owns its streams, events and a 256 kB staging block.  The batch is cut into `chunks`
+ * pieces (boundaries grow like c^1.5) and H2D(actions) | step + export kernels | D2H(results) are overlapped; the call
+ * returns when the host arrays are filled.  Batches whose results fit the staging block are instead packed on the
+ * device and leave in one transfer on `caller_stream` (`obs_dev` is not written then).  Page-locked host memory
+ * (sdcgym_host_alloc, cudaHostAlloc, torch pin_memory) makes the copies asynchronous; pageable memory works but
+ * serialises them.  NULL host outputs are skipped.
  */
 typedef struct sdcgym_pipe sdcgym_pipe;
 typedef struct sdcgym_host_io {

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstring>
 #include <new>
 
 #include "../../include/sdcgym.h"
@@ -19,7 +20,48 @@ struct sdcgym_pipe {
     cudaEvent_t* ev_in;   // [max_chunks] actions of chunk c are on the device
     cudaEvent_t* ev_k;    // [max_chunks] kernels of chunk c are done
     cudaEvent_t ev_start;
+    // small batches: all results are packed into one device block and leave in ONE transfer (pipe-owned staging)
+    unsigned char* pack_dev;
+    unsigned char* pack_host;
 };
+
+// Batches whose results fit this many bytes take the packed path (six ~7 us transfers become one).
+constexpr size_t kPackBytes = 256 * 1024;
+
+struct PackLayout {
+    size_t obs, reward, residual, lam, niter, flags, total;  // byte offsets inside the block
+};
+static PackLayout pack_layout(int M, int64_t N) {
+    PackLayout L;
+    size_t o = 0;
+    L.obs = o;      o += (size_t)N * 4 * M * sizeof(double);
+    L.reward = o;   o += (size_t)N * sizeof(double);
+    L.residual = o; o += (size_t)N * sizeof(double);
+    L.lam = o;      o += (size_t)N * 2 * sizeof(double);
+    L.niter = o;    o += ((size_t)N * sizeof(int32_t) + 7) / 8 * 8;
+    L.flags = o;    o += ((size_t)N + 7) / 8 * 8;
+    L.total = o;
+    return L;
+}
+
+// one thread per env: observation planes -> reference layout [env][u|r][m][re|im], plus the per-env result scalars
+__global__ void pack_results_kernel(int M, int64_t N, int64_t ld, const double* __restrict__ S,
+                                    const double* __restrict__ reward, const double* __restrict__ residual,
+                                    const double* __restrict__ lam, const int32_t* __restrict__ niter,
+                                    const uint8_t* __restrict__ flags, unsigned char* __restrict__ block, PackLayout L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double* obs = reinterpret_cast<double*>(block + L.obs) + i * 4 * M;
+    for (int p = 0; p < 4 * M; p++) obs[p] = S[p * ld + i];
+    if (reward) reinterpret_cast<double*>(block + L.reward)[i] = reward[i];
+    if (residual) reinterpret_cast<double*>(block + L.residual)[i] = residual[i];
+    if (lam) {
+        reinterpret_cast<double*>(block + L.lam)[2 * i] = lam[2 * i];
+        reinterpret_cast<double*>(block + L.lam)[2 * i + 1] = lam[2 * i + 1];
+    }
+    if (niter) reinterpret_cast<int32_t*>(block + L.niter)[i] = niter[i];
+    if (flags) (block + L.flags)[i] = flags[i];
+}
 
 #define PIPE_CHECK(x)                       \
     do {                                    \
@@ -46,6 +88,8 @@ extern "C" int sdcgym_pipe_create(int max_chunks, sdcgym_pipe** out) {
         PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_in[c], cudaEventDisableTiming));
         PIPE_CHECK(cudaEventCreateWithFlags(&p->ev_k[c], cudaEventDisableTiming));
     }
+    PIPE_CHECK(cudaMalloc((void**)&p->pack_dev, kPackBytes));
+    PIPE_CHECK(cudaHostAlloc((void**)&p->pack_host, kPackBytes, cudaHostAllocDefault));
     *out = p;
     return 0;
 }
@@ -65,6 +109,8 @@ extern "C" int sdcgym_pipe_destroy(sdcgym_pipe* p) {
     cudaStreamDestroy(p->s_k);
     cudaStreamDestroy(p->s_out);
     cudaStreamDestroy(p->s_out2);
+    cudaFree(p->pack_dev);
+    cudaFreeHost(p->pack_host);
     delete[] p->ev_in;
     delete[] p->ev_k;
     delete p;
@@ -98,6 +144,39 @@ extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, con
     if (A > 0 && (!host->action || !dev->action)) return SDCGYM_ENULL;
     if (host->obs && !obs_dev) return SDCGYM_ENULL;
     cudaStream_t cs = (cudaStream_t)caller_stream;
+
+    // ---- small batch: upload, step, pack, ONE download, scatter on the host.  Runs on the caller's stream. ----
+    const PackLayout L = pack_layout(M, N);
+    if (L.total <= kPackBytes) {
+        double* act_dev = const_cast<double*>(dev->action);
+        sdcgym_step_io io = *dev;
+        if (A > 0) {
+            PIPE_CHECK(cudaMemcpyAsync(act_dev, host->action, sizeof(double) * N * aw, cudaMemcpyHostToDevice, cs));
+            io.action_env_stride = aw;
+            io.action_comp_stride = desc->action_is_complex ? 2 : 1;
+        } else {
+            io.action = nullptr;
+        }
+        int rc = sdcgym_step(desc, st, &io, cs);
+        if (rc) return rc;
+        pack_results_kernel<<<(unsigned)((N + 127) / 128), 128, 0, cs>>>(
+            M, N, st->ld, st->S, host->reward ? dev->reward : nullptr, host->residual ? dev->info_residual : nullptr,
+            host->lam ? dev->info_lam : nullptr, host->niter ? dev->info_niter : nullptr,
+            host->flags ? dev->flags : nullptr, p->pack_dev, L);
+        PIPE_CHECK(cudaGetLastError());
+        const size_t first = host->obs ? 0 : L.reward;  // skip the observation part when nobody wants it
+        PIPE_CHECK(cudaMemcpyAsync(p->pack_host + first, p->pack_dev + first, L.total - first, cudaMemcpyDeviceToHost, cs));
+        PIPE_CHECK(cudaStreamSynchronize(cs));
+        const unsigned char* b = p->pack_host;
+        if (host->obs) memcpy(host->obs, b + L.obs, (size_t)N * 4 * M * sizeof(double));
+        if (host->reward && dev->reward) memcpy(host->reward, b + L.reward, (size_t)N * sizeof(double));
+        if (host->residual && dev->info_residual) memcpy(host->residual, b + L.residual, (size_t)N * sizeof(double));
+        if (host->lam && dev->info_lam) memcpy(host->lam, b + L.lam, (size_t)N * 2 * sizeof(double));
+        if (host->niter && dev->info_niter) memcpy(host->niter, b + L.niter, (size_t)N * sizeof(int32_t));
+        if (host->flags && dev->flags) memcpy(host->flags, b + L.flags, (size_t)N);
+        return 0;
+    }
+
     // everything the caller enqueued before this call happens before the pipeline starts
     PIPE_CHECK(cudaEventRecord(p->ev_start, cs));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));

@@ -272,6 +272,7 @@ class SDCVecEnv:
             raise ValueError("host_pipeline must be 'native' (sdcgym_pipe_step) or 'torch' (torch streams)")
         self.host_pipeline = host_pipeline
         self._pipe = None
+        self._pipe_args = None
 
         self._desc = _lib.EnvDesc()
         d = self._desc
@@ -520,6 +521,14 @@ class SDCVecEnv:
                 lam=torch.zeros((N, 2), dtype=torch.float64, **pin),
             )
             self._host["actions"].append(self._host["action"])
+            # numpy views are built once: tensor.numpy() / .view() per step would cost more than a small batch's kernels
+            h = self._host
+            h["np"] = dict(
+                obs=h["obs"].numpy().view(np.complex128).reshape(N, 2, M), reward=h["reward"].numpy(),
+                flags=h["flags"].numpy(), niter=h["niter"].numpy(), residual=h["residual"].numpy(),
+                lam=h["lam"].numpy().view(np.complex128).reshape(N))
+            h["action_np"] = [h["action"].numpy()]
+            h["action_ptr"] = [h["action"].data_ptr()]
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         return self._host
 
@@ -530,6 +539,8 @@ class SDCVecEnv:
         host = self._ensure_host()
         while len(host["actions"]) <= index:
             host["actions"].append(_torch().zeros_like(host["action"]).pin_memory())
+            host["action_np"].append(host["actions"][-1].numpy())
+            host["action_ptr"].append(host["actions"][-1].data_ptr())
         a = host["actions"][index].numpy()
         if self.free_action_space:
             return a.view(np.complex128)
@@ -547,10 +558,11 @@ class SDCVecEnv:
                 raise TypeError("complex actions need free_action_space=True")
             a = np.asarray(a, dtype=np.float64).reshape(self.num_envs, self._kernel_n_act)
         ptr = a.__array_interface__["data"][0]
-        for t in host["actions"]:
-            if t.data_ptr() == ptr and a.flags.c_contiguous:
-                return t
-        np.copyto(host["actions"][0].numpy(), a)
+        if a.flags.c_contiguous:
+            for t, tp in zip(host["actions"], host["action_ptr"]):
+                if tp == ptr:
+                    return t
+        np.copyto(host["action_np"][0], a)
         return host["actions"][0]
 
     def step_async(self, actions):
@@ -588,18 +600,21 @@ class SDCVecEnv:
                 handle = ctypes.c_void_p()
                 _lib.check(self._L.sdcgym_pipe_create(64, ctypes.byref(handle)), "sdcgym_pipe_create")
                 self._pipe = handle
-            io = _lib.StepIO()
-            io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
-            io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
-            io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
-            io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
-            hio = _lib.HostIO()
+            if self._pipe_args is None:
+                # the device / pinned buffers never move: build the argument structs once
+                io = _lib.StepIO()
+                io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
+                io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
+                io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
+                io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
+                hio = _lib.HostIO()
+                hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
+                hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
+                self._pipe_args = (io, hio, self._state(), self.obs_aos.data_ptr())
+            io, hio, st, obs_dev = self._pipe_args
             hio.action = src.data_ptr() if src is not None else None
-            hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
-            hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
-            st = self._state()
             _lib.check(self._L.sdcgym_pipe_step(self._pipe, ctypes.byref(self._desc), ctypes.byref(st), ctypes.byref(io),
-                                                self.obs_aos.data_ptr(), ctypes.byref(hio), chunks, self._stream()),
+                                                obs_dev, ctypes.byref(hio), chunks, self._stream()),
                        "sdcgym_pipe_step")
             self._invalidate()
             return self._host_outputs(host)
@@ -656,14 +671,15 @@ class SDCVecEnv:
     def _host_outputs(self, host):
         N = self.num_envs
         cp = (lambda x: x) if self.reuse_buffers else np.copy
-        obs = cp(host["obs"].numpy().view(np.complex128).reshape(N, 2, self.M))
-        rewards = cp(host["reward"].numpy())
-        flags = cp(host["flags"].numpy())
+        v = host["np"]
+        obs = cp(v["obs"])
+        rewards = cp(v["reward"])
+        flags = cp(v["flags"])
         dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
-        niter = cp(host["niter"].numpy())
-        lam = cp(host["lam"].numpy()).view(np.complex128).reshape(N)
+        niter = cp(v["niter"])
+        lam = cp(v["lam"])
         truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
-        infos = LazyInfos(niter, cp(host["residual"].numpy()), lam, dones, truncated_key, self._fetch_terminal)
+        infos = LazyInfos(niter, cp(v["residual"]), lam, dones, truncated_key, self._fetch_terminal)
         infos.flags = flags
         return obs, rewards, dones, infos
 
@@ -748,6 +764,7 @@ class SDCVecEnv:
 
     def close(self):
         self._host = None
+        self._pipe_args = None
         if self._pipe is not None:
             self._L.sdcgym_pipe_destroy(self._pipe)
             self._pipe = None
