@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 1
+#define SDCGYM_ABI_VERSION 2
 #define SDCGYM_MAX_M 9
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -155,14 +155,16 @@ int sdcgym_refresh_resnorm(int M, int64_t N, int64_t ld, const double* S, double
  * complex (interleaved) parameters in get_qdmat's layout (dp_playground.py:194-207); for SDCGYM_PREC_FIXED
  * `qd` is ignored and Qd_fixed (real M x M) is used.  rho: [N].
  * If lam == NULL, lambdas are the nodes of a (grid_re x grid_im) tensor grid over [re_lo,re_hi] x [im_lo,im_hi]
- * (N = grid_re*grid_im, row-major over re then im, end points included) and qd, if given, has a single row.
+ * (row-major over re then im, end points included) and qd, if given, has a single row.  The call evaluates the N
+ * nodes with flat indices grid_first .. grid_first+N-1 (grid_first = 0, N = grid_re*grid_im: the whole grid), so that
+ * ranks can shard the grid by rows and all-reduce one scalar for the mean loss.
  */
 typedef struct sdcgym_rho_desc {
     int32_t M, prec_type, qd_is_complex, qd_broadcast;
     double dt;
     double Q[SDCGYM_MAX_M * SDCGYM_MAX_M];
     double Qd_fixed[SDCGYM_MAX_M * SDCGYM_MAX_M];
-    int64_t grid_re, grid_im;
+    int64_t grid_re, grid_im, grid_first;
     double re_lo, re_hi, im_lo, im_hi;
 } sdcgym_rho_desc;
 int sdcgym_spectral_radius(const sdcgym_rho_desc* desc, int64_t N, const double* lam, const double* qd, double* rho,

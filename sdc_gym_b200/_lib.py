@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
 
 MAX_M = 9
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -107,6 +107,7 @@ class RhoDesc(ctypes.Structure):
         ("Qd_fixed", ctypes.c_double * (MAX_M * MAX_M)),
         ("grid_re", ctypes.c_int64),
         ("grid_im", ctypes.c_int64),
+        ("grid_first", ctypes.c_int64),
         ("re_lo", ctypes.c_double),
         ("re_hi", ctypes.c_double),
         ("im_lo", ctypes.c_double),

@@ -16,7 +16,7 @@ struct RhoParams {
     const double* qd;   // [N][A](x2) or one row (broadcast) or NULL
     double* rho;
     double dt;
-    int64_t grid_re, grid_im;
+    int64_t grid_re, grid_im, grid_first;
     double re_lo, re_hi, im_lo, im_hi;
     int32_t prec_type, qd_is_complex, qd_broadcast, n_act;
 };
@@ -29,7 +29,8 @@ SDCGYM_HD bool rho_inputs(const RhoParams<M>& p, int64_t i, double& lr, double& 
         li = p.lam[2 * i + 1];
     } else {
         // tensor grid, row-major over (re, im), end points included (np.linspace semantics)
-        int64_t a = i / p.grid_im, b = i - a * p.grid_im;
+        const int64_t g = p.grid_first + i;
+        int64_t a = g / p.grid_im, b = g - a * p.grid_im;
         lr = (p.grid_re > 1) ? p.re_lo + (p.re_hi - p.re_lo) * ((double)a / (double)(p.grid_re - 1)) : p.re_lo;
         li = (p.grid_im > 1) ? p.im_lo + (p.im_hi - p.im_lo) * ((double)b / (double)(p.grid_im - 1)) : p.im_lo;
     }
@@ -113,6 +114,7 @@ inline void fill_rho_params(RhoParams<M>& p, const sdcgym_rho_desc* d, int64_t N
     p.dt = d->dt;
     p.grid_re = d->grid_re;
     p.grid_im = d->grid_im;
+    p.grid_first = d->grid_first;
     p.re_lo = d->re_lo;
     p.re_hi = d->re_hi;
     p.im_lo = d->im_lo;

@@ -141,31 +141,53 @@ class SpectralRadiusLoss:
         ``requires_grad``) - forward and backward both run the hand-written kernels."""
         return _SpectralRadiusFn.apply(outputs, self, lams)
 
-    def mean(self, rho):
+    def _sum(self, rho):
+        """deterministic fp64 sum (fixed reduction tree) as a CUDA scalar"""
         torch = _torch()
-        out = torch.empty(1, dtype=torch.float64, device=self.device)
-        scratch = torch.empty(self._L.sdcgym_sum_scratch_doubles(), dtype=torch.float64, device=self.device)
-        _lib.check(self._L.sdcgym_sum_f64(rho.numel(), rho.data_ptr(), scratch.data_ptr(), out.data_ptr(),
-                                          self._stream()), "sdcgym_sum_f64")
-        return out[0] / rho.numel()
+        out = torch.zeros(1, dtype=torch.float64, device=self.device)
+        if rho.numel():
+            scratch = torch.empty(self._L.sdcgym_sum_scratch_doubles(), dtype=torch.float64, device=self.device)
+            _lib.check(self._L.sdcgym_sum_f64(rho.numel(), rho.data_ptr(), scratch.data_ptr(), out.data_ptr(),
+                                              self._stream()), "sdcgym_sum_f64")
+        return out[0]
 
-    def grid(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None):
+    def mean(self, rho):
+        return self._sum(rho) / rho.numel()
+
+    def grid(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None, rows=None):
         """rho on the (n_re x n_im) tensor grid over the lambda box for ONE Q_delta parameter row (or the fixed
         ``prec``): lambdas are generated from the grid index on the device (0 bytes in, 8 bytes out per matrix).
-        Returns a CUDA tensor (n_re, n_im)."""
+        ``rows=(lo, hi)`` evaluates only the grid rows lo..hi-1 (real-axis index) - the shard of one rank.
+        Returns a CUDA tensor (n_re, n_im) [(hi - lo, n_im) with ``rows``]."""
         torch = _torch()
         qd, is_c, _ = self._outputs_tensor(output, 1) if self.prec is None else (None, 0, 0)
+        lo, hi = (0, int(n_re)) if rows is None else (int(rows[0]), int(rows[1]))
+        if not 0 <= lo <= hi <= int(n_re):
+            raise ValueError(f"rows={rows} outside the grid of {n_re} rows")
         d = self._desc
         d.qd_is_complex, d.qd_broadcast = is_c, 1
-        d.grid_re, d.grid_im = int(n_re), int(n_im)
+        d.grid_re, d.grid_im, d.grid_first = int(n_re), int(n_im), lo * int(n_im)
         d.re_lo, d.re_hi = float(lambda_real_interval[0]), float(lambda_real_interval[1])
         d.im_lo, d.im_hi = float(lambda_imag_interval[0]), float(lambda_imag_interval[1])
-        N = int(n_re) * int(n_im)
+        N = (hi - lo) * int(n_im)
         rho = torch.empty(N, dtype=torch.float64, device=self.device)
         _lib.check(self._L.sdcgym_spectral_radius(ctypes.byref(d), N, None, None if qd is None else qd.data_ptr(),
                                                   rho.data_ptr(), self._stream()), "sdcgym_spectral_radius")
+        d.grid_first = 0
         self._keep = (qd,)
-        return rho.reshape(n_re, n_im)
+        return rho.reshape(hi - lo, n_im)
+
+    def grid_mean(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None):
+        """Mean of rho over the grid with the rows sharded over the ranks of the default process group:
+        every rank evaluates ``dist.shard_range(n_re)`` rows and ONE scalar is all-reduced.  Without an initialised
+        process group this is the single-GPU mean.  Returns a CUDA scalar (the same value on every rank)."""
+        from . import dist as _dist
+
+        rank, world = _dist.world()
+        lo, count = _dist.shard_range(int(n_re), rank, world)
+        rho = self.grid(n_re, n_im, lambda_real_interval, lambda_imag_interval, output, rows=(lo, lo + count))
+        total = _dist.all_reduce_sum(self._sum(rho.reshape(-1)).reshape(1))[0]
+        return total / (int(n_re) * int(n_im))
 
 
 def _make_autograd_fn():

@@ -228,6 +228,13 @@ def test_spectral_radius_grid_and_fixed_prec():
             l = complex(re[a], im[b])
             ref = max(abs(np.linalg.eigvals(l * np.linalg.inv(np.eye(M) - l * np.diag(x)) @ (Q - np.diag(x)))))
             assert abs(g[a, b] - ref) <= 1e-10 * max(ref, 1e-3)
+    # row shards of the grid (one per rank in a multi-GPU run) are the rows of the full grid, bit for bit
+    parts = [loss.grid(33, 17, [-100, 0], [-10, 0], x, rows=r).cpu().numpy() for r in ((0, 11), (11, 12), (12, 12), (12, 33))]
+    assert [p.shape for p in parts] == [(11, 17), (1, 17), (0, 17), (21, 17)]
+    assert np.array_equal(np.concatenate(parts), g)
+    assert float(loss.grid_mean(33, 17, [-100, 0], [-10, 0], x)) == pytest.approx(g.mean(), rel=1e-14)
+    with pytest.raises(ValueError):
+        loss.grid(33, 17, [-100, 0], [-10, 0], x, rows=(5, 34))
     for prec in ("LU", "min", "EE", "zeros"):
         lossf = SpectralRadiusLoss(M, 1.0, prec=prec)
         lam = np.array([-50 - 3j, -1 - 0.5j, -99.5 - 9j])

@@ -1,7 +1,9 @@
 """Multi-GPU correctness check (run under torchrun, one rank per GPU):
   1. every rank's shard of a global batch reproduces, bit for bit, its slice of the same batch stepped on one GPU;
   2. VecNormalize statistics synchronised over NCCL equal the single-GPU statistics to reduction-order accuracy;
-  3. RolloutStats.reduce() equals the single-GPU totals.
+  3. RolloutStats.reduce() equals the single-GPU totals;
+  4. the spectral-radius grid sharded by rows (SpectralRadiusLoss.grid_mean, one scalar all-reduced) has the mean of
+     the full grid evaluated on one GPU.
 torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_sharding.py"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -49,6 +51,22 @@ for kind in ("sdc-v0", "sdc-v1"):
         print(json.dumps({"kind": kind, "world": ws, "global_envs": NG, "steps": len(acts), "bit_equal_shards": bool(ok),
                           "obs_mean_maxabs_diff": dm, "obs_var_maxrel_diff": dv, "ret_var_rel_diff": dr,
                           "rollout": red}), flush=True)
+# ---- 4. rho grid sharded by rows ----
+from sdc_gym_b200.loss import SpectralRadiusLoss
+from sdc_gym_b200.precond import fixed_preconditioner
+loss = SpectralRadiusLoss(5, 1.0, "diag")
+x = np.diag(fixed_preconditioner("min", 5))
+G_RE, G_IM = 1001, 257  # rows not divisible by the world size
+full_grid = loss.grid(G_RE, G_IM, [-100, 0], [-10, 0], x)
+lo, cnt_rows = sdist.shard_range(G_RE, rank, ws)
+mine = loss.grid(G_RE, G_IM, [-100, 0], [-10, 0], x, rows=(lo, lo + cnt_rows))
+ok &= bool(torch.equal(mine, full_grid[lo:lo + cnt_rows]))
+m_sharded = float(loss.grid_mean(G_RE, G_IM, [-100, 0], [-10, 0], x))
+m_full = float(loss.mean(full_grid.reshape(-1)))
+ok &= abs(m_sharded - m_full) <= 1e-13 * abs(m_full)
+if rank == 0:
+    print(json.dumps({"kind": "rho grid", "world": ws, "grid": [G_RE, G_IM], "rows_bit_equal": bool(ok),
+                      "mean_sharded": m_sharded, "mean_single_gpu": m_full}), flush=True)
 flag = torch.tensor([1.0 if bool(ok) else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
