@@ -78,6 +78,12 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         SDCGYM_TVS(35, 6, 9, 64)
         SDCGYM_TVS(36, 6, 7, 64)
         SDCGYM_TVS(37, 4, 7, 64)
+        SDCGYM_TVS(40, 7, 4, 128)
+        SDCGYM_TVS(41, 7, 5, 128)
+        SDCGYM_TVS(42, 7, 5, 96)
+        SDCGYM_TVS(43, 7, 8, 64)
+        SDCGYM_TVS(44, 7, 3, 128)
+        SDCGYM_TVS(45, 7, 6, 64)
 #undef SDCGYM_TVS
 #undef SDCGYM_TV
         default: break;

@@ -258,6 +258,17 @@ SDCGYM_HD HiBand make_band(double t) {
 #define SDCGYM_WARP_ANY(x) (x)
 #endif
 
+// one 128-bit shared-memory load of a (re, im) pair; volatile so that it stays a load inside the sweep loop
+SDCGYM_HD cplx ld_pair(const cplx* p) {
+#ifdef __CUDA_ARCH__
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 template <int M, int KIND, int V, bool DENSE, int HOLD>
 SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1,
                         cplx* pside = nullptr, const int pstride = 1) {
@@ -265,7 +276,49 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     const int64_t i = valid ? tid : p.N - 1;
     const int64_t ld = p.ld;
 
-    const double lr = p.lam[i], li = p.lam[ld + i];
+    // ---- phase 0: every global load of this env is issued here, in one basic block, so that a single DRAM round trip
+    //      covers them all (placed at their uses they end up behind the branches of the division slow paths, one
+    //      exposed latency each) ----
+    double lr = p.lam[i], li = p.lam[ld + i];
+    double araw[DENSE ? 1 : M], aimg[DENSE ? 1 : M];
+    if (!DENSE) {
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            araw[k] = 0.0;
+            aimg[k] = 0.0;
+            if (p.prec_type != SDCGYM_PREC_FIXED) {
+                araw[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                if (p.is_complex) aimg[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
+            }
+        }
+    }
+    double ur[M], ui[M], rr[M], ri[M];
+    auto load_state = [&]() {
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            ur[m] = p.S[(2 * m) * ld + i];
+            ui[m] = p.S[(2 * m + 1) * ld + i];
+            rr[m] = p.S[(2 * M + 2 * m) * ld + i];
+            ri[m] = p.S[(2 * M + 2 * m + 1) * ld + i];
+        }
+    };
+    if (!DENSE) load_state();  // the dense kernels need the registers for the inverse first
+    double nr_old = p.resnorm[i];
+    int it = (KIND == SDCGYM_ENV_STEP) ? p.niter[i] : 0;
+    // the auto-reset needs these at the very end
+    int32_t ep_old = p.autoreset ? p.episodes[i] : 0;
+    uint32_t ctr_old = p.autoreset ? p.rng_ctr[i] : 0u;
+#ifdef __CUDA_ARCH__
+    // consume everything here: keeps the loads above this point.  (Not for the dense kernels: they load the Q_delta
+    // entries next and a barrier here would only add a second exposed round trip - measured 20 % slower at M = 3.)
+    if (!DENSE) {
+        asm volatile("" : "+d"(lr), "+d"(li), "+d"(nr_old), "+r"(it), "+r"(ep_old), "+r"(ctr_old));
+#pragma unroll
+        for (int k = 0; k < M; k++) asm volatile("" : "+d"(araw[k]), "+d"(aimg[k]));
+#pragma unroll
+        for (int m = 0; m < M; m++) asm volatile("" : "+d"(ur[m]), "+d"(ui[m]), "+d"(rr[m]), "+d"(ri[m]));
+    }
+#endif
     const double zr = dmul(lr, p.dt), zi = dmul(li, p.dt);
 
     // ---- preconditioner inverse ----
@@ -283,10 +336,10 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 const double d = p.Qd[k * M + k];
                 zq = cplx{dmul(zr, d), dmul(zi, d)};
             } else if (p.is_complex) {
-                cplx d{ld_ro(p.action + i * p.a_es + k * p.a_cs), ld_ro(p.action + i * p.a_es + k * p.a_cs + 1)};
+                cplx d{araw[DENSE ? 0 : k], aimg[DENSE ? 0 : k]};
                 zq = cmul_np(cplx{zr, zi}, d);
             } else {
-                double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                double a = araw[DENSE ? 0 : k];
                 double d = a;
                 if (p.do_scale) d = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
                 zq = cplx{dmul(zr, d), dmul(zi, d)};
@@ -410,22 +463,13 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 if (CS) side[(M * M + r * M + c) * side_stride] = crv;
                 if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
                 if (HOLD == 3 || CS) side[(r * M + c) * side_stride] = -dmul(zi, q);
-                if (HOLD == 5) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
+                if (HOLD == 5 || HOLD == 7) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
                 if (HOLD == 6) side[(r * M + c) * side_stride] = crv;
             }
     }
 
-    // ---- state ----
-    double ur[M], ui[M], rr[M], ri[M];
-#pragma unroll
-    for (int m = 0; m < M; m++) {
-        ur[m] = p.S[(2 * m) * ld + i];
-        ui[m] = p.S[(2 * m + 1) * ld + i];
-        rr[m] = p.S[(2 * M + 2 * m) * ld + i];
-        ri[m] = p.S[(2 * M + 2 * m + 1) * ld + i];
-    }
-    const double nr_old = p.resnorm[i];
-    int it = (KIND == SDCGYM_ENV_STEP) ? p.niter[i] : 0;
+
+    if (DENSE) load_state();
 
     // sdc-v1 needs the previous residual for the reward when norm_factor != 1
     double norm_old_scaled = nr_old;
@@ -480,12 +524,16 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
 #pragma unroll
             for (int c = 0; c < M; c++) {
                 double q = p.Q[m * M + c];
-                if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
+                cplx t7{0.0, 0.0};
+                if (HOLD == 7) t7 = ld_pair(&pside[(m * M + c) * pstride]);  // HOLD 7: C as (re, im) pairs, one LDS.128
+                if (HOLD == 7) cr[c] = t7.re;
+                else if (HOLD == 5) cr[c] = vp[(m * M + c) * pstride].re;
                 else if (HOLD == 6) cr[c] = vside[(m * M + c) * side_stride];
                 else if (CS) cr[c] = vside[(M * M + m * M + c) * side_stride];
                 else if (HOLD >= 1 && HOLD != 9) cr[c] = Cr[(HOLD >= 1 && HOLD <= 3) ? m * M + c : 0];
                 else cr[c] = (m == c) ? dsub(1.0, dmul(zr_s, q)) : -dmul(zr_s, q);
-                if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
+                if (HOLD == 7) ci[c] = t7.im;
+                else if (HOLD == 5) ci[c] = vp[(m * M + c) * pstride].im;
                 else if (HOLD == 6) ci[c] = -dmul(zi_s, q);
                 else if (HOLD == 2) ci[c] = Ci[(HOLD == 2) ? m * M + c : 0];
                 else if (HOLD == 3 || CS) ci[c] = vside[(m * M + c) * side_stride];
@@ -592,9 +640,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
 
     if (done && p.autoreset) {
         // DummyVecEnv: obs = env.reset() right after the terminal step
-        int32_t ep = p.episodes[i] + 1;
+        int32_t ep = ep_old + 1;
         p.episodes[i] = ep;
-        uint32_t ctr = p.rng_ctr[i];
+        uint32_t ctr = ctr_old;
         double nlr, nli;
         draw_lambda<M>(p, i, ctr, ep, nlr, nli);
         p.rng_ctr[i] = ctr + 1;
@@ -620,7 +668,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
 
 template <int M, int KIND, int V, bool DENSE, int HOLD, int MINB = 1, int BLOCK = kBlock>
 __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant__ StepParams<M> p) {
-    if constexpr (HOLD == 5) {
+    if constexpr (HOLD == 5 || HOLD == 7) {
         extern __shared__ double2 pside_smem[];  // [2*M*M][BLOCK] complex: LU/C then Pinv of every thread
         step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x, nullptr, 1,
                                           reinterpret_cast<cplx*>(pside_smem) + threadIdx.x, BLOCK);
@@ -635,7 +683,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
 template <int M, int HOLD, int BLOCK = kBlock>
 constexpr size_t step_kernel_smem_bytes() {
     return HOLD == 3 ? (size_t)M * M * BLOCK * sizeof(double)
-                     : ((HOLD == 4 || HOLD == 8 || HOLD == 9) ? (size_t)2 * M * M * BLOCK * sizeof(double)
+                     : ((HOLD == 4 || HOLD == 7 || HOLD == 8 || HOLD == 9) ? (size_t)2 * M * M * BLOCK * sizeof(double)
                                   : (HOLD == 5 ? (size_t)4 * M * M * BLOCK * sizeof(double)
                                                : (HOLD == 6 ? (size_t)M * M * BLOCK * sizeof(double) : 0)));
 }

@@ -74,6 +74,12 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
 //  * M <= 4: C is small enough to stay in registers.
 //  * dense kernels spend their registers on the M x M inverse; sdc-v1 runs one sweep per launch and is memory
 //    bound: nothing is held, occupancy is maximised.
+#ifndef SDCGYM_DIAG_MID
+#define SDCGYM_DIAG_MID 7  // residency of the M = 5..7 diagonal kernels (4 or 7)
+#endif
+#ifndef SDCGYM_DENSE_SMALL
+#define SDCGYM_DENSE_SMALL 7  // residency of the M = 4, 5 dense kernels (4 or 7; 7 measured 2-4 % faster)
+#endif
 #ifndef SDCGYM_DENSE_MID
 #define SDCGYM_DENSE_MID 9  // residency of the M = 6, 7 dense kernels (0 or 9)
 #endif
@@ -85,16 +91,18 @@ inline void fill_step_io(StepParams<M>& p, const sdcgym_step_io* io) {
 #endif
 template <int M>
 struct HoldPolicy {
-    static constexpr int diag = (M <= 4) ? 1 : ((M <= 7) ? 4 : 0);  // M >= 8: 2 blocks of 64 threads lose to recomputing
+    // M = 5..7: C in shared memory as (re, im) pairs read with one LDS.128 (HOLD 7; planar HOLD 4 was 2.8 % slower);
+    // M >= 8: 2 blocks of 64 threads lose to recomputing
+    static constexpr int diag = (M <= 4) ? 1 : ((M <= 7) ? SDCGYM_DIAG_MID : 0);
     static constexpr int diag_minb = (M <= 5) ? 4 : 2;
     static constexpr int diag_block = 128;
     // dense kernels: M <= 5 keep the inverse in registers and C in shared memory (HOLD 4); M = 6, 7 run the inverse on
     // register-resident LU factors and re-derive C (HOLD 0); M = 8, 9 keep the LU work matrix, then Pinv, in shared
     // memory and re-derive C (HOLD 9; HOLD 8 = C instead of Pinv there measured 25 % slower) in 64-thread blocks.  (Keeping Pinv in shared memory as well - HOLD 5, parity-tested - leaves
     // only 2-4 warps per SM and measured slower than letting Pinv spill to local memory.)
-    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? 4 : ((M <= 7) ? SDCGYM_DENSE_MID : SDCGYM_DENSE_BIG));
+    static constexpr int dense = (M <= 3) ? 2 : ((M <= 5) ? SDCGYM_DENSE_SMALL : ((M <= 7) ? SDCGYM_DENSE_MID : SDCGYM_DENSE_BIG));
     static constexpr int dense_block = (M <= 7) ? 128 : 64;
-    static constexpr int dense_minb = (M == 4 || M == 5) ? SDCGYM_DENSE_MINB : 2;
+    static constexpr int dense_minb = (M <= 5) ? SDCGYM_DENSE_MINB : 2;  // 168 registers: 3 blocks/SM (170 would round up to 176 = 2 blocks)
     static constexpr int step = 0;
     static constexpr int step_minb = (M <= 5) ? 6 : ((M <= 7) ? 3 : 2);  // M=5: 80 regs, 24 warps/SM: +12 % (profiles/tune_r01_v1.log)
 };

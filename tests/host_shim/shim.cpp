@@ -65,11 +65,11 @@ static int step_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym
     cplx pside[2 * 2 * M * M];  // complex side store of HOLD == 5 (stride 2)
     for (int64_t i = 0; i < nthreads; i++) {
         if (d->blas_variant == 0) {
-            if (full) { if (dense) step_one<M, 0, 0, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 0, 0, false, HD>(p, i, side, 2); }
-            else      { if (dense) step_one<M, 1, 0, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 1, 0, false, HV1>(p, i, side, 2); }
+            if (full) { if (dense) step_one<M, 0, 0, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 0, 0, false, HD>(p, i, side, 2, pside, 2); }
+            else      { if (dense) step_one<M, 1, 0, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 1, 0, false, HV1>(p, i, side, 2, pside, 2); }
         } else {
-            if (full) { if (dense) step_one<M, 0, 1, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 0, 1, false, HD>(p, i, side, 2); }
-            else      { if (dense) step_one<M, 1, 1, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 1, 1, false, HV1>(p, i, side, 2); }
+            if (full) { if (dense) step_one<M, 0, 1, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 0, 1, false, HD>(p, i, side, 2, pside, 2); }
+            else      { if (dense) step_one<M, 1, 1, true, HS>(p, i, side, 2, pside, 2); else step_one<M, 1, 1, false, HV1>(p, i, side, 2, pside, 2); }
         }
     }
     return 0;
