@@ -72,6 +72,11 @@ extern "C" {
 #define SDCGYM_FLAG_CONVERGED 2 /* ||r|| < restol */
 #define SDCGYM_FLAG_ERR 4       /* NaN/Inf or residual grew > 100x (sdc_env.py:234,241,527,532) */
 
+/* bits of sdcgym_env_desc.do_scale (0 / 1 as before; bit 1 added for use_doubles=False) */
+#define SDCGYM_ACTION_SCALE 1 /* do_scale: map real actions [-1,1] -> [0,1] (sdc_env.py:125-132) */
+#define SDCGYM_ACTION_F32 2   /* use_doubles=False: Q_delta entries are stored in the float32/complex64 action
+                               * dtype (sdc_env.py:100,109,138-140): the scaled action is rounded to float32 */
+
 /* OpenBLAS core whose rounding sequence is reproduced */
 #define SDCGYM_BLAS_SKYLAKEX 0
 #define SDCGYM_BLAS_HASWELL 1
@@ -82,7 +87,7 @@ typedef struct sdcgym_env_desc {
     int32_t env_kind;          /* SDCGYM_ENV_* */
     int32_t prec_type;         /* SDCGYM_PREC_* */
     int32_t action_is_complex; /* free_action_space: actions are (re, im) pairs */
-    int32_t do_scale;          /* map real actions [-1,1] -> [0,1] (sdc_env.py:125-132) */
+    int32_t do_scale;          /* SDCGYM_ACTION_* bits: scale real actions [-1,1] -> [0,1]; float32 Q_delta */
     int32_t max_iters;         /* 50 (sdc_env.py:25) */
     int32_t reward_strategy;   /* SDCGYM_REW_* */
     int32_t blas_variant;      /* SDCGYM_BLAS_* */

@@ -109,11 +109,12 @@ def reset(Q, dt, lam, variant=0):
 
 def step(kind, Q, dt, lam, u, r, niter, rinit, action, *, prec_type="diag", Qd_fixed=None, do_scale=True,
          reward_strategy="iteration_only", step_penalty=0.1, residual_weight=0.5, norm_factor=1.0,
-         restol=1e-10, max_iters=50, variant=0, collect_states=None, want_pinv=False):
+         restol=1e-10, max_iters=50, variant=0, collect_states=None, want_pinv=False, use_doubles=True):
     """Advance N envs in place (u, r, niter are modified).  Returns dict(reward, done, resnorm, err[, pinv]).
 
     ``kind`` is 'sdc-v0' or 'sdc-v1'.  For 'sdc-v0', ``done`` is the *converged* flag (the env itself always
-    reports done=True, ``sdc_env.py:259``).
+    reports done=True, ``sdc_env.py:259``).  ``use_doubles=False``: float32 / complex64 action space, i.e. the
+    learned Q_delta entries are rounded to float32 (``sdc_env.py:100,109,138-140``).
     """
     Q = np.ascontiguousarray(Q, np.float64)
     M = Q.shape[0]
@@ -147,7 +148,7 @@ def step(kind, Q, dt, lam, u, r, niter, rinit, action, *, prec_type="diag", Qd_f
         extra = collect_states
         if extra is not None:
             assert extra.dtype == np.complex128 and extra.shape == (N, 2 * M, max_iters) and extra.flags.c_contiguous
-    fn(M, _d(Q), float(dt), N, pt, _d(Qd_fixed), _d(act), is_c, int(bool(do_scale)), _d(lam),
+    fn(M, _d(Q), float(dt), N, pt, _d(Qd_fixed), _d(act), is_c, int(bool(do_scale)) | (0 if use_doubles else 2), _d(lam),
        _d(u), _d(r), niter.ctypes.data_as(_ip), _d(rinit),
        REWARD_STRATEGIES[reward_strategy], float(step_penalty), float(residual_weight), float(norm_factor),
        float(restol), int(max_iters),

@@ -365,10 +365,22 @@ static void build_Qd(int M, int prec_type, const cplx *d, const double *Qd_fixed
 
 /* P = eye(M) - (lam*dt)*Qd  (sdc_env.py:198-200).  Real Qd: numpy multiplies the complex scalar with a
  * float array (cast to complex, imaginary part +0) - the ufunc loop is the same cmul. */
-static void build_P(int M, cplx z, const cplx *Qd, cplx *P) {
+/* use_doubles=False: Qdmat is float32 / complex64 and lam*dt a Python complex, so numpy evaluates the product
+ * in complex64 (operands rounded to float32, same fused loop form in float arithmetic); `eye(M) - ...`
+ * promotes the result to complex128 exactly. */
+static cplx cmul_np_f32(cplx a, cplx b) {
+    float ar = (float)a.re, ai = (float)a.im, br = (float)b.re, bi = (float)b.im;
+    float t1 = ai * bi, t2 = ai * br;
+    cplx c;
+    c.re = (double)fmaf(ar, br, -t1);
+    c.im = (double)fmaf(ar, bi, t2);
+    return c;
+}
+
+static void build_P(int M, cplx z, const cplx *Qd, cplx *P, int f32) {
     for (int i = 0; i < M; i++)
         for (int j = 0; j < M; j++) {
-            cplx zq = cmul_np(z, Qd[i * M + j]);
+            cplx zq = f32 ? cmul_np_f32(z, Qd[i * M + j]) : cmul_np(z, Qd[i * M + j]);
             P[i * M + j].re = (i == j ? 1.0 : 0.0) - zq.re;
             P[i * M + j].im = 0.0 - zq.im;
         }
@@ -458,7 +470,7 @@ static void get_scaled_action(int A, const double *action, int action_is_complex
             d[k].im = action[(e * A + k) * 2 + 1];
         } else {
             double a = action[e * A + k];
-            d[k].re = do_scale ? scale_action(a) : a;
+            d[k].re = (do_scale & 1) ? scale_action(a) : a;
             d[k].im = 0.0;
         }
     }
@@ -486,7 +498,7 @@ void sdc_oracle_step_v1(int M, const double *Q, double dt, int64_t N, int prec_t
         build_C(M, Q, z, C);
         get_scaled_action(A, action, action_is_complex, do_scale, e, d);
         build_Qd(M, prec_type, d, Qd_fixed, Qd);
-        build_P(M, z, Qd, P);
+        build_P(M, z, Qd, P, (do_scale & 2) && prec_type != PREC_FIXED);
         sdc_oracle_cinv(M, (const double *)P, (double *)Pinv, variant);
         if (Pinv_out) memcpy(Pinv_out + e * M * M * 2, Pinv, sizeof(cplx) * M * M);
         memcpy(old_r, r, sizeof(cplx) * M);
@@ -536,7 +548,7 @@ void sdc_oracle_step_v0(int M, const double *Q, double dt, int64_t N, int prec_t
         build_C(M, Q, z, C);
         get_scaled_action(A, action, action_is_complex, do_scale, e, d);
         build_Qd(M, prec_type, d, Qd_fixed, Qd);
-        build_P(M, z, Qd, P);
+        build_P(M, z, Qd, P, (do_scale & 2) && prec_type != PREC_FIXED);
         sdc_oracle_cinv(M, (const double *)P, (double *)Pinv, variant);
         double nr_old = inf_norm(r, M), nr = nr_old;
         int dn = 0, err = 0, it = 0;

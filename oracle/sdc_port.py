@@ -39,8 +39,8 @@ class PortFullEnv:
     def __init__(self, M=None, dt=None, restol=None, prec=None, seed=None, lambda_real_interval=(-100, 0),
                  lambda_imag_interval=(0, 0), lambda_real_interpolation_interval=None, norm_factor=1,
                  residual_weight=0.5, step_penalty=0.1, reward_iteration_only=None,
-                 reward_strategy="iteration_only", collect_states=False, do_scale=True, free_action_space=False,
-                 prec_type="diag"):
+                 reward_strategy="iteration_only", collect_states=False, use_doubles=True, do_scale=True,
+                 free_action_space=False, prec_type="diag"):
         self.M, self.dt, self.restol, self.prec = M, dt, restol, prec
         self.coll = CollGaussRadauRight(M, 0, 1)
         self.Q = self.coll.Qmat[1:, 1:]
@@ -57,7 +57,10 @@ class PortFullEnv:
         else:
             self.reward_strategy = "residual_change"
         self.collect_states, self.do_scale = collect_states, do_scale
-        self.action_dtype = np.complex128 if free_action_space else np.float64
+        if free_action_space:  # sdc_env.py:95-110
+            self.action_dtype = np.complex128 if use_doubles else np.complex64
+        else:
+            self.action_dtype = np.float64 if use_doubles else np.float32
         self.prec_type = prec_type
         self.num_episodes = 0
         self.np_random = np.random.RandomState(seed)
@@ -81,10 +84,10 @@ class PortFullEnv:
                 Qdmat = np.zeros_like(self.Q, dtype=self.action_dtype)
                 np.fill_diagonal(Qdmat, scaled_action)
             elif self.prec_type == "lower_diag":
-                Qdmat = np.diag(np.asarray(scaled_action), k=-1)
+                Qdmat = np.diag(np.asarray(scaled_action).astype(self.action_dtype), k=-1)
             else:
                 out = np.asarray(scaled_action)
-                Qdmat = np.zeros((M, M), dtype=out.dtype)
+                Qdmat = np.zeros((M, M), dtype=self.action_dtype)
                 idx = np.tril_indices(M) if self.prec_type == "lower_tri" else np.tril_indices(M, k=-1)
                 Qdmat[idx] = out
         elif self.prec.upper() == "LU":

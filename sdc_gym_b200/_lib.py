@@ -26,6 +26,7 @@ REWARD_STRATEGIES = {
 }
 FLAG_DONE, FLAG_CONVERGED, FLAG_ERR = 1, 2, 4
 BLAS_SKYLAKEX, BLAS_HASWELL = 0, 1
+ACTION_SCALE, ACTION_F32 = 1, 2  # bits of EnvDesc.do_scale (include/sdcgym.h)
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 

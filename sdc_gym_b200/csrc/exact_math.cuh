@@ -64,6 +64,23 @@ SDCGYM_HD cplx cmul_np(cplx a, cplx b) {
     c.im = dfma(a.re, b.im, dmul(a.im, b.re));
     return c;
 }
+// use_doubles=False (float32 / complex64 action space, sdc_env.py:100,109): Qdmat is allocated in the action dtype
+// (:138-140), so `fill_diagonal` rounds the scaled action to float32, and `self.lam * self.dt * Qdmat` (:199) - a
+// Python complex (lam is built from Python floats, :293-300) times a float32/complex64 array - is evaluated by numpy
+// in complex64: operands rounded to float32, same fused loop form as above in float arithmetic.  `eye(M) - ...`
+// then promotes the product to complex128 exactly.
+SDCGYM_HD cplx cmul_np_f32(cplx a, cplx b) {
+    const float ar = (float)a.re, ai = (float)a.im, br = (float)b.re, bi = (float)b.im;
+    cplx c;
+#ifdef __CUDA_ARCH__
+    c.re = (double)__fmaf_rn(ar, br, -__fmul_rn(ai, bi));
+    c.im = (double)__fmaf_rn(ar, bi, __fmul_rn(ai, br));
+#else
+    c.re = (double)fmaf(ar, br, -(ai * bi));
+    c.im = (double)fmaf(ar, bi, ai * br);
+#endif
+    return c;
+}
 SDCGYM_HD cplx cmul_unfused(cplx a, cplx b) {
     cplx c;
     c.re = dsub(dmul(a.re, b.re), dmul(a.im, b.im));

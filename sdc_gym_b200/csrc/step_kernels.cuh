@@ -339,12 +339,12 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 zq = cplx{dmul(zr, d), dmul(zi, d)};
             } else if (p.is_complex) {
                 cplx d{araw[DENSE ? 0 : k], aimg[DENSE ? 0 : k]};
-                zq = cmul_np(cplx{zr, zi}, d);
+                zq = (p.do_scale & SDCGYM_ACTION_F32) ? cmul_np_f32(cplx{zr, zi}, d) : cmul_np(cplx{zr, zi}, d);
             } else {
                 double a = araw[DENSE ? 0 : k];
                 double d = a;
-                if (p.do_scale) d = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
-                zq = cplx{dmul(zr, d), dmul(zi, d)};
+                if (p.do_scale & SDCGYM_ACTION_SCALE) d = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
+                zq = (p.do_scale & SDCGYM_ACTION_F32) ? cmul_np_f32(cplx{zr, zi}, cplx{d, 0.0}) : cplx{dmul(zr, d), dmul(zi, d)};
             }
             pre_r[DENSE ? 0 : k] = dsub(1.0, zq.re);
             pre_i[DENSE ? 0 : k] = -zq.im;
@@ -374,7 +374,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 } else {
                     const double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
                     d.re = a;
-                    if (p.do_scale) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
+                    if (p.do_scale & SDCGYM_ACTION_SCALE) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
                 }
             }
             return d;
@@ -389,13 +389,18 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             default: return -1;
             }
         };
+        const bool f32_qd = (p.do_scale & SDCGYM_ACTION_F32) && p.prec_type != SDCGYM_PREC_FIXED;
+        auto zq_entry = [&](int r, int c) {
+            const cplx d = qd_entry(r, c, act_index(r, c));
+            return f32_qd ? cmul_np_f32(cplx{zr, zi}, d) : cmul_np(cplx{zr, zi}, d);
+        };
         if constexpr (M <= kRegInvMaxM) {
             RegMatrix<M> A;
 #pragma unroll
             for (int r = 0; r < M; r++)
 #pragma unroll
                 for (int c = 0; c < M; c++) {
-                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    const cplx zq = zq_entry(r, c);
                     A.R(r, c) = dsub((r == c) ? 1.0 : 0.0, zq.re);
                     A.I(r, c) = dsub(0.0, zq.im);
                 }
@@ -412,7 +417,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             for (int r = 0; r < M; r++)
 #pragma unroll
                 for (int c = 0; c < M; c++) {
-                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    const cplx zq = zq_entry(r, c);
                     A.R(r, c) = dsub((r == c) ? 1.0 : 0.0, zq.re);
                     A.I(r, c) = dsub(0.0, zq.im);
                 }
@@ -427,7 +432,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             for (int r = 0; r < M; r++)
 #pragma unroll 1
                 for (int c = 0; c < M; c++) {
-                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    const cplx zq = zq_entry(r, c);
                     A[(r + c * M) * pstride] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
                 }
             cinv_exact<M, V>(A, B, pstride);
@@ -437,7 +442,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             for (int r = 0; r < M; r++)
 #pragma unroll 1
                 for (int c = 0; c < M; c++) {
-                    const cplx zq = cmul_np(cplx{zr, zi}, qd_entry(r, c, act_index(r, c)));
+                    const cplx zq = zq_entry(r, c);
                     A[r + c * M] = cplx{dsub((r == c) ? 1.0 : 0.0, zq.re), dsub(0.0, zq.im)};
                 }
             cinv_exact<M, V>(A, B);

@@ -309,10 +309,11 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
             } else {
                 const double a = ld_ro(p.action + i * p.a_es + k * p.a_cs);
                 d.re = a;
-                if (p.do_scale) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
+                if (p.do_scale & SDCGYM_ACTION_SCALE) d.re = (a <= -1.0) ? 0.0 : ((a >= 1.0) ? 1.0 : dmul(0.5, dadd(a, 1.0)));
             }
         }
-        const cplx zq = cmul_np(cplx{zr, zi}, d);
+        const cplx zq = ((p.do_scale & SDCGYM_ACTION_F32) && p.prec_type != SDCGYM_PREC_FIXED)
+                            ? cmul_np_f32(cplx{zr, zi}, d) : cmul_np(cplx{zr, zi}, d);
         ar[c] = dsub((row == c) ? 1.0 : 0.0, zq.re);
         ai[c] = dsub(0.0, zq.im);
     }

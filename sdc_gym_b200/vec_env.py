@@ -197,9 +197,10 @@ class SDCVecEnv:
             raise TypeError("M, dt and restol are required (as in the reference constructor)")
         if not torch.cuda.is_available():
             raise _lib.SdcGymError("SDCVecEnv needs a CUDA device: the SDC kernels have no CPU fallback")
-        if not use_doubles:
-            raise NotImplementedError("use_doubles=False (float32 action space) is not supported; "
-                                      "the kernels compute in fp64 like the reference env")
+        # use_doubles=False (SAC, utils/utils.py:279-280): float32 / complex64 action space; the reference then stores
+        # Q_delta in that dtype (sdc_env.py:138-140) and sweeps in complex128 - the kernels round the scaled action to
+        # float32 (SDCGYM_ACTION_F32) and compute in fp64 as before
+        self.use_doubles = bool(use_doubles)
         self._L = _lib.load()
         self.envname = envname
         self.num_envs = int(num_envs)
@@ -236,9 +237,9 @@ class SDCVecEnv:
         obs_shape = (self.M * 2, self.max_iters) if collect_states else (2, self.M)
         self.observation_space = Box(-1e10, 1e10, obs_shape, np.complex128)
         if free_action_space:
-            self.action_space = Box(-np.inf, np.inf, (self.n_act,), np.complex128)
+            self.action_space = Box(-np.inf, np.inf, (self.n_act,), np.complex128 if use_doubles else np.complex64)
         else:
-            self.action_space = Box(-1.0, 1.0, (self.n_act,), np.float64)
+            self.action_space = Box(-1.0, 1.0, (self.n_act,), np.float64 if use_doubles else np.float32)
 
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         N = self.num_envs
@@ -278,11 +279,15 @@ class SDCVecEnv:
         d = self._desc
         d.M, d.env_kind = self.M, _lib.ENV_KINDS[envname]
         d.prec_type = _lib.PREC_TYPES[self.prec_type]
-        d.action_is_complex, d.do_scale = int(self.free_action_space), int(self.do_scale)
+        d.action_is_complex = int(self.free_action_space)
+        d.do_scale = (_lib.ACTION_SCALE if self.do_scale else 0) | (0 if self.use_doubles else _lib.ACTION_F32)
         d.max_iters = self.max_iters
         # 'spectral_radius' (sdc_env.py:421-425) is composed from two kernels: the step runs with the cheapest
         # in-kernel reward and `_apply_spectral_radius_reward` overwrites it with rho from the eigenvalue kernel
         self._rho_reward = self.reward_strategy == "spectral_radius"
+        if self._rho_reward and not self.use_doubles and prec is None:
+            raise NotImplementedError("reward_strategy='spectral_radius' with use_doubles=False: the eigenvalue kernel "
+                                      "forms P in complex128, the reference's float32 Q_delta path does not")
         d.reward_strategy = _lib.REWARD_STRATEGIES["iteration_only" if self._rho_reward else self.reward_strategy]
         d.blas_variant = detect_blas_variant() if blas_variant is None else int(blas_variant)
         d.autoreset = int(self.autoreset and not self.collect_states)

@@ -38,6 +38,9 @@ def subclass_with_layout(cls, prec_type):
         def _get_prec(self, scaled_action):
             M = self.M
             out = np.asarray(scaled_action)
+            if self.action_space.dtype in (np.float32, np.complex64):
+                # use_doubles=False: same storage rule as the reference's own diagonal branch (sdc_env.py:138-140)
+                out = out.astype(self.action_space.dtype)
             if prec_type == "lower_diag":
                 return np.diag(out, k=-1)
             Qd = np.zeros((M, M), dtype=out.dtype)
@@ -60,7 +63,7 @@ MIN_DIAG = {
 
 def run_case(name, kind, M, n, rng, *, prec=None, prec_type="diag", dt=1.0, restol=1e-10, cplx=False, do_scale=True,
              strategy="iteration_only", norm_factor=1, action_mode="uniform", collect=False,
-             re_int=(-100, 0), im_int=(-10, 0), step_penalty=0.1, residual_weight=0.5):
+             re_int=(-100, 0), im_int=(-10, 0), step_penalty=0.1, residual_weight=0.5, use_doubles=True):
     mod = ref_loader.load_reference_envs()
     cls = mod.SDC_Full_Env if kind == "sdc-v0" else mod.SDC_Step_Env
     if prec is None and prec_type != "diag":
@@ -85,7 +88,7 @@ def run_case(name, kind, M, n, rng, *, prec=None, prec_type="diag", dt=1.0, rest
         env = cls(M=M, dt=dt, restol=restol, prec=prec, lambda_real_interval=list(re_int),
                   lambda_imag_interval=list(im_int), reward_iteration_only=None, reward_strategy=strategy,
                   norm_factor=norm_factor, do_scale=do_scale, free_action_space=cplx, collect_states=collect,
-                  step_penalty=step_penalty, residual_weight=residual_weight)
+                  step_penalty=step_penalty, residual_weight=residual_weight, use_doubles=use_doubles)
         # NB: env.Q stays the reference's own (non-contiguous) view of Qmat.  Handing it a C-contiguous copy
         # would let `scipy.linalg.lu(Q.T, overwrite_a=True)` (sdc_env.py:142-143) overwrite Q in place.
         assert np.array_equal(env.Q, Q)
@@ -104,7 +107,9 @@ def run_case(name, kind, M, n, rng, *, prec=None, prec_type="diag", dt=1.0, rest
             else:
                 a = rng.uniform(0, 0.6, A)
             if a is not None:
-                actions[e, s] = a
+                if not use_doubles:  # SB3 hands the env actions in the action-space dtype (float32 / complex64)
+                    a = a.astype(env.action_space.dtype)
+                actions[e, s] = a  # stored as float64 / complex128 (exact)
             _, reward, d, info = env.step(None if a is None else a.copy())
             U[e, s], R[e, s] = env.state[0], env.state[1]
             res[e, s], nit[e, s], rew[e, s], done[e, s] = info["residual"], info["niter"], reward, d
@@ -119,7 +124,8 @@ def run_case(name, kind, M, n, rng, *, prec=None, prec_type="diag", dt=1.0, rest
         out["old_states"] = old_states
     meta = dict(name=name, kind=kind, M=M, n=n, prec=prec, prec_type=prec_type if prec is None else "fixed", dt=dt,
                 restol=restol, cplx=cplx, do_scale=do_scale, strategy=strategy, norm_factor=norm_factor,
-                collect=collect, step_penalty=step_penalty, residual_weight=residual_weight)
+                collect=collect, step_penalty=step_penalty, residual_weight=residual_weight,
+                use_doubles=use_doubles)
     return meta, out
 
 
@@ -157,6 +163,21 @@ def main():
             action_mode="good", norm_factor=3.7)
         add(f"{tag}_diag_M5_collect", kind, 5, 3, rng, action_mode="good", collect=True)
         add(f"{tag}_LU_M5_collect", kind, 5, 2, rng, prec="LU", collect=True)
+
+    # use_doubles=False (float32 / complex64 action space, utils/utils.py:279-280 for SAC): appended with their own
+    # generator so the cases above keep their bits
+    rng = np.random.default_rng(20261019)
+    for kind, nn in (("sdc-v0", 12), ("sdc-v1", 4)):
+        tag = kind[-2:]
+        for M in (3, 5, 9):
+            add(f"{tag}_diag_M{M}_f32", kind, M, nn, rng, use_doubles=False)
+        add(f"{tag}_diag_M5_good_f32", kind, 5, nn, rng, use_doubles=False, action_mode="good")
+        add(f"{tag}_diag_M5_noscale_f32", kind, 5, 4, rng, use_doubles=False, do_scale=False)
+        add(f"{tag}_diag_cplx_M5_c64", kind, 5, 4, rng, use_doubles=False, cplx=True, do_scale=False)
+        add(f"{tag}_lower_tri_M5_f32", kind, 5, 4, rng, use_doubles=False, prec_type="lower_tri", do_scale=False)
+        add(f"{tag}_lower_tri_M9_f32", kind, 9, 3, rng, use_doubles=False, prec_type="lower_tri", do_scale=False)
+        add(f"{tag}_strictly_lower_tri_cplx_M7_c64", kind, 7, 3, rng, use_doubles=False, cplx=True,
+            prec_type="strictly_lower_tri", do_scale=False)
 
     from threadpoolctl import threadpool_info
     blas = [i for i in threadpool_info() if i.get("internal_api") == "openblas"]

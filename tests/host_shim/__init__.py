@@ -52,11 +52,12 @@ def shim():
 
 def make_desc(kind, M, *, prec=None, prec_type="diag", dt=1.0, restol=1e-10, cplx=False, do_scale=True,
               strategy="iteration_only", step_penalty=0.1, residual_weight=0.5, norm_factor=1.0, variant=0,
-              autoreset=False, Q=None, seed=0, env_offset=0, re_int=(-100, 0), im_int=(-10, 0), curriculum=None):
+              autoreset=False, Q=None, seed=0, env_offset=0, re_int=(-100, 0), im_int=(-10, 0), curriculum=None,
+              use_doubles=True):
     d = _lib.EnvDesc()
     d.M, d.env_kind = M, _lib.ENV_KINDS[kind]
     d.prec_type = _lib.PREC_TYPES["fixed" if prec is not None else prec_type]
-    d.action_is_complex, d.do_scale, d.max_iters = int(cplx), int(do_scale), 50
+    d.action_is_complex, d.do_scale, d.max_iters = int(cplx), int(bool(do_scale)) | (0 if use_doubles else 2), 50
     d.reward_strategy = _lib.REWARD_STRATEGIES[strategy]
     d.blas_variant, d.autoreset = variant, int(autoreset)
     d.dt, d.restol = dt, restol

@@ -20,7 +20,8 @@ class CudaBackend:
         self.env = sdc_gym_b200.make(
             meta["kind"], num_envs=meta["n"], M=meta["M"], dt=meta["dt"], restol=meta["restol"], prec=meta["prec"],
             prec_type=meta["prec_type"] if meta["prec"] is None else "diag", free_action_space=meta["cplx"],
-            do_scale=meta["do_scale"], reward_iteration_only=None, reward_strategy=meta["strategy"],
+            do_scale=meta["do_scale"], use_doubles=meta.get("use_doubles", True), reward_iteration_only=None,
+            reward_strategy=meta["strategy"],
             step_penalty=meta["step_penalty"], residual_weight=meta["residual_weight"], norm_factor=meta["norm_factor"],
             collect_states=meta["collect"], Q=g["Q"], blas_variant=_lib.BLAS_SKYLAKEX, autoreset=False,
             lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0])

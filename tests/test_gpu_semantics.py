@@ -313,8 +313,8 @@ def test_ragged_batch_sizes_and_extreme_M(n, M):
 def test_unsupported_configurations_fail_loudly():
     with pytest.raises(NotImplementedError):
         sdc_gym_b200.make("sdc-v0", num_envs=4, **{**KW, "M": 10})
-    with pytest.raises(NotImplementedError):
-        sdc_gym_b200.make("sdc-v0", num_envs=4, use_doubles=False, **KW)
+    with pytest.raises(NotImplementedError):  # float32 Q_delta + eigenvalue reward: not composed (vec_env.py)
+        sdc_gym_b200.make("sdc-v0", num_envs=4, use_doubles=False, reward_strategy="spectral_radius", **KW)
     with pytest.raises(NotImplementedError):
         sdc_gym_b200.make("sdc-v0", num_envs=4, reward_strategy="nope", **KW)
     env = sdc_gym_b200.make("sdc-v0", num_envs=4, **KW)
@@ -323,6 +323,36 @@ def test_unsupported_configurations_fail_loudly():
         env.step(np.zeros((4, 3)))
     with pytest.raises(TypeError):
         env.step(np.zeros((4, 5), np.complex128))
+
+
+def test_use_doubles_false_action_space_and_parity():
+    """use_doubles=False (SAC, utils/utils.py:279-280): float32 / complex64 action space (sdc_env.py:95-110); the
+    reference then forms lam*dt*Qdmat in complex64 (golden cases *_f32 / *_c64 pin the arithmetic); here a larger
+    batch against the rounding-exact oracle, fed with float32 arrays like SB3 would."""
+    n, M = 3000, 5
+    rng = np.random.default_rng(21)
+    Q = collocation_matrix(M)
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+    for kind in ("sdc-v0", "sdc-v1"):
+        env = sdc_gym_b200.make(kind, num_envs=n, use_doubles=False, autoreset=False, **KW)
+        assert env.action_space.dtype == np.float32 and env.action_space.shape == (M,)
+        env.reset(lam=lam)
+        u, r = exact.reset(Q, 1.0, lam)
+        xmin = np.diag(fixed_preconditioner("min", M))
+        act = (2 * (xmin[None] + rng.uniform(-0.02, 0.02, (n, M))) - 1).astype(np.float32)
+        _, rew, done, infos = env.step(act)
+        nit = np.zeros(n, np.int32)
+        o = exact.step(kind, Q, 1.0, lam, u, r, nit, r.copy(), act.astype(np.float64), use_doubles=False)
+        snap = env._snapshot()
+        assert_same(snap["obs"][:, 0], u); assert_same(snap["obs"][:, 1], r)
+        assert np.array_equal(infos.niter, nit)
+        assert_same(infos.residual, o["resnorm"])
+        # and it is a different result from the float64 action space on the same numbers
+        u2, r2 = exact.reset(Q, 1.0, lam)
+        exact.step(kind, Q, 1.0, lam, u2, r2, np.zeros(n, np.int32), r2.copy(), act.astype(np.float64))
+        assert not np.array_equal(u, u2)
+    envc = sdc_gym_b200.make("sdc-v1", num_envs=4, use_doubles=False, free_action_space=True, do_scale=False, **KW)
+    assert envc.action_space.dtype == np.complex64
 
 
 def test_spectral_radius_reward_strategy():

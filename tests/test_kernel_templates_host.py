@@ -14,6 +14,7 @@ class ShimBackend:
     def __init__(self, meta, g):
         d = host_shim.make_desc(meta["kind"], meta["M"], prec=meta["prec"], prec_type=meta["prec_type"] if meta["prec"] is None else "diag",
                                 dt=meta["dt"], restol=meta["restol"], cplx=meta["cplx"], do_scale=meta["do_scale"],
+                                use_doubles=meta.get("use_doubles", True),
                                 strategy=meta["strategy"], step_penalty=meta["step_penalty"],
                                 residual_weight=meta["residual_weight"], norm_factor=meta["norm_factor"], Q=g["Q"])
         self.b = host_shim.ShimBatch(d, meta["n"], collect=meta["collect"])

@@ -32,7 +32,8 @@ def replay_with_oracle(name):
     for s in range(steps_max):
         act = g["actions"][:, s, :A] if A else None
         out = exact.step(kind, Q, meta["dt"], g["lam"], u, r, niter, rinit, act, prec_type=meta["prec_type"],
-                         Qd_fixed=Qd_fixed, do_scale=meta["do_scale"], reward_strategy=meta["strategy"],
+                         Qd_fixed=Qd_fixed, do_scale=meta["do_scale"], use_doubles=meta.get("use_doubles", True),
+                         reward_strategy=meta["strategy"],
                          step_penalty=meta["step_penalty"], residual_weight=meta["residual_weight"],
                          norm_factor=meta["norm_factor"], restol=meta["restol"], variant=0, collect_states=old_states)
         live = alive & (s < g["nsteps"])

@@ -26,7 +26,7 @@ def test_port_replays_golden(name):
     for e in range(meta["n"]):
         env = sdc_port.ENV_CLASSES[kind](
             M=M, dt=meta["dt"], restol=meta["restol"], prec=meta["prec"], reward_iteration_only=None,
-            reward_strategy=meta["strategy"], norm_factor=meta["norm_factor"], do_scale=meta["do_scale"],
+            reward_strategy=meta["strategy"], norm_factor=meta["norm_factor"], do_scale=meta["do_scale"], use_doubles=meta.get("use_doubles", True),
             free_action_space=meta["cplx"], collect_states=meta["collect"], step_penalty=meta["step_penalty"],
             residual_weight=meta["residual_weight"], prec_type=meta["prec_type"] if meta["prec"] is None else "diag")
         env.niter = 0
