@@ -213,6 +213,15 @@ int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, con
                               double* sums, void* stream);
 int sdcgym_vecnorm_merge(int P, double batch_count, const double* sums, double* mean, double* var, double* count2,
                          void* stream);
+/* Single-rank fast path: accumulate + merge (+ commit) in ONE launch, bit-identical to the sequence above (the last
+ * block folds the partial sums in index order).  `scratch` must be zero-initialised once (it holds a ticket word the
+ * kernel resets itself) and `sdcgym_vecnorm_scratch_doubles(P)` doubles long.  `_update_returns` also advances the
+ * discounted returns in the same pass: returns <- returns * gamma + reward, then updates the return statistics
+ * (mean/var/count2 of ONE plane; scratch sized for P = 1). */
+int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var, double* count2,
+                          double* scratch, double* sums, void* stream);
+int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, double gamma, double* returns, double* mean,
+                                  double* var, double* count2, double* scratch, double* sums, void* stream);
 int sdcgym_vecnorm_apply(int P, int64_t N, int64_t ld, const double* X, const double* mean, const double* var, double eps,
                          double clip, double* Y, void* stream);
 int sdcgym_vecnorm_returns(int64_t N, const double* reward, double gamma, double* returns, void* stream);

@@ -174,6 +174,8 @@ def load():
     L.sdcgym_vecnorm_scratch_doubles.argtypes = [ctypes.c_int]
     L.sdcgym_vecnorm_accumulate.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_merge.argtypes = [ctypes.c_int, dbl, vp, vp, vp, vp, vp]
+    L.sdcgym_vecnorm_update.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.sdcgym_vecnorm_update_returns.argtypes = [i64, vp, dbl, vp, vp, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_apply.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, dbl, dbl, vp, vp]
     L.sdcgym_vecnorm_returns.argtypes = [i64, vp, dbl, vp, vp]
     L.sdcgym_vecnorm_reward.argtypes = [i64, vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
@@ -188,7 +190,7 @@ def load():
     L.sdcgym_gae.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     L.sdcgym_gae.restype = ctypes.c_int
     for name in ("sdcgym_residual_step", "sdcgym_vecnorm_scratch_doubles", "sdcgym_vecnorm_accumulate",
-                 "sdcgym_vecnorm_merge", "sdcgym_vecnorm_apply", "sdcgym_vecnorm_returns", "sdcgym_vecnorm_reward"):
+                 "sdcgym_vecnorm_merge", "sdcgym_vecnorm_update", "sdcgym_vecnorm_update_returns", "sdcgym_vecnorm_apply", "sdcgym_vecnorm_returns", "sdcgym_vecnorm_reward"):
         getattr(L, name).restype = ctypes.c_int
     for name in ("sdcgym_num_actions", "sdcgym_supported", "sdcgym_reset", "sdcgym_step", "sdcgym_export_obs",
                  "sdcgym_import_obs", "sdcgym_refresh_resnorm", "sdcgym_sum_f64", "sdcgym_fp64_peak_probe",

@@ -39,6 +39,28 @@ __device__ __forceinline__ double2 block_sum2(double a, double b) {
     return make_double2(a, b);
 }
 
+// The statistics arithmetic is spelled with explicit roundings so that every kernel that performs it (the
+// three-kernel sequence and the fused single-launch update) produces the same bits whatever the compiler contracts.
+__device__ __forceinline__ void acc_one(double x, double s, double& a, double& b) {
+    const double d = __dsub_rn(x, s);
+    a = __dadd_rn(a, d);
+    b = __fma_rn(d, d, b);
+}
+__device__ __forceinline__ double advance_return(double ret, double gamma, double reward) {
+    return __fma_rn(ret, gamma, reward);
+}
+// RunningMeanStd.update_from_moments with the batch given as shifted sums (shift = the running mean itself)
+__device__ __forceinline__ void rms_merge_one(double n, double batch, double sa, double sb, double& mean, double& var) {
+    const double d1 = __ddiv_rn(sa, batch);  // batch_mean - running mean
+    const double d1sq = __dmul_rn(d1, d1);
+    const double bvar = fmax(__dsub_rn(__ddiv_rn(sb, batch), d1sq), 0.0);  // population variance of the batch
+    const double tot = __dadd_rn(n, batch);
+    const double cross = __ddiv_rn(__dmul_rn(__dmul_rn(d1sq, n), batch), tot);
+    const double m2 = __dadd_rn(__dadd_rn(__dmul_rn(var, n), __dmul_rn(bvar, batch)), cross);
+    mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(d1, batch), tot));
+    var = __ddiv_rn(m2, tot);
+}
+
 // partial[(p*kAccBlocks + b)*2 + {0,1}] = sum over this block's strided slice of (x - shift_p), (x - shift_p)^2
 __global__ void __launch_bounds__(kAccThreads) acc_partial_kernel(int64_t N, int64_t ld, const double* __restrict__ X,
                                                                   const double* __restrict__ shift,
@@ -48,9 +70,7 @@ __global__ void __launch_bounds__(kAccThreads) acc_partial_kernel(int64_t N, int
     const double* x = X + (int64_t)p * ld;
     double a = 0.0, b = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < N; i += (int64_t)kAccBlocks * kAccThreads) {
-        const double d = x[i] - s;
-        a += d;
-        b += d * d;
+        acc_one(x[i], s, a, b);
     }
     double2 r = block_sum2(a, b);
     if (threadIdx.x == 0) {
@@ -76,17 +96,74 @@ __global__ void rms_merge_kernel(int P, double batch_count, const double* __rest
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const double n = count[0];
     if (p < P && batch_count > 0) {
-        const double d1 = sums[p] / batch_count;                 // batch_mean - running mean
-        const double bvar = fmax(sums[P + p] / batch_count - d1 * d1, 0.0);  // population variance of the batch
-        const double tot = n + batch_count;
-        const double m2 = var[p] * n + bvar * batch_count + d1 * d1 * n * batch_count / tot;
-        mean[p] = mean[p] + d1 * batch_count / tot;
-        var[p] = m2 / tot;
+        double m = mean[p], v = var[p];
+        rms_merge_one(n, batch_count, sums[p], sums[P + p], m, v);
+        mean[p] = m;
+        var[p] = v;
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && batch_count > 0) count[1] = n + batch_count;  // committed by the host-side swap
 }
 __global__ void rms_commit_kernel(double* __restrict__ count) { count[0] = count[1]; }
+
+// ---- single-rank fast path: accumulate + fold + merge in ONE launch ----------------------------------------------
+// Same partial sums as acc_partial_kernel (same slices, same tree), then the block that finishes last folds the
+// kAccBlocks partials of every plane in index order and applies the merge - bit-identical to the three-kernel
+// sequence accumulate -> merge -> commit, without the three launches (a normalised sdc-v1 step of 2^20 envs is a
+// 115 us kernel: five 2-7 us launches per statistic were a fifth of the step).
+// RETURNS: the plane is the discounted return, advanced in the same pass: ret <- ret * gamma + reward.
+template <bool RETURNS>
+__global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
+                                                             const double* __restrict__ reward, double gamma,
+                                                             double* __restrict__ ret, double* mean, double* var,
+                                                             double* count, double* __restrict__ partial,
+                                                             double* __restrict__ sums, unsigned int* ticket) {
+    const int p = blockIdx.y;
+    const double s = mean[p];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < N; i += (int64_t)kAccBlocks * kAccThreads) {
+        double x;
+        if (RETURNS) {
+            x = advance_return(ret[i], gamma, reward[i]);
+            ret[i] = x;
+        } else {
+            x = X[(int64_t)p * ld + i];
+        }
+        acc_one(x, s, a, b);
+    }
+    double2 r = block_sum2(a, b);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const double n = count[0], batch = (double)N;
+    __syncthreads();
+    for (int q = threadIdx.x; q < P; q += kAccThreads) {
+        double sa = 0.0, sb = 0.0;
+        for (int k = 0; k < kAccBlocks; k++) {
+            sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
+            sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+        }
+        sums[q] = sa;
+        sums[P + q] = sb;
+        double m = mean[q], v = var[q];
+        rms_merge_one(n, batch, sa, sb, m, v);
+        mean[q] = m;
+        var[q] = v;
+    }
+    if (threadIdx.x == 0) {
+        count[0] = n + batch;
+        count[1] = n + batch;
+        *ticket = 0u;  // self-cleaning: ready for the next launch on this stream
+    }
+}
 
 __global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X, const double* __restrict__ mean,
                              const double* __restrict__ var, double eps, double clip, double* __restrict__ Y) {
@@ -100,7 +177,7 @@ __global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X
 
 __global__ void returns_kernel(int64_t N, const double* __restrict__ reward, double gamma, double* __restrict__ ret) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) ret[i] = ret[i] * gamma + reward[i];
+    if (i < N) ret[i] = advance_return(ret[i], gamma, reward[i]);
 }
 __global__ void reward_apply_kernel(int64_t N, const double* __restrict__ reward, const uint8_t* __restrict__ flags,
                                     const double* __restrict__ ret_var, double eps, double clip, int normalize,
@@ -296,7 +373,29 @@ extern "C" int sdcgym_gae(int T, int64_t N, const double* rewards, const double*
     return (int)cudaGetLastError();
 }
 
-extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2; }
+extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2 + 2; }  // partials + the ticket word
+
+extern "C" int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
+                                     double* count2, double* scratch, double* sums, void* stream) {
+    if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!X || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)P * kAccBlocks * 2);
+    update_kernel<false><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
+        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, double gamma, double* returns, double* mean,
+                                             double* var, double* count2, double* scratch, double* sums, void* stream) {
+    if (N < 0) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!reward || !returns || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
+    update_kernel<true><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
+        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift,
                                          double* scratch, double* sums, void* stream) {

@@ -21,14 +21,18 @@ def _torch():
 
 class RolloutBuffer:
     def __init__(self, n_steps, num_envs, obs_planes, action_dim, device, gamma=0.99, gae_lambda=0.95,
-                 obs_dtype=None, action_is_complex=False):
+                 obs_dtype=None, action_is_complex=False, ld=None):
         torch = _torch()
         self.n_steps, self.num_envs, self.P, self.A = int(n_steps), int(num_envs), int(obs_planes), int(action_dim)
         self.gamma, self.gae_lambda = float(gamma), float(gae_lambda)
         self.device = torch.device(device)
         f64 = torch.float64
         T, N = self.n_steps, self.num_envs
-        self.observations = torch.zeros((T, self.P, N), dtype=obs_dtype or f64, device=self.device)
+        # observation slots keep the env's plane stride `ld` so that a slot can be the direct output of the
+        # normalisation kernel (VecNormalize.step_tensor(obs_out=slot)); `observations` is the (T, P, N) view
+        self.ld = N if ld is None else int(ld)
+        self.obs_store = torch.zeros((T, self.P, self.ld), dtype=obs_dtype or f64, device=self.device)
+        self.observations = self.obs_store[:, :, :N]
         self.actions = torch.zeros((T, N, self.A), dtype=torch.complex128 if action_is_complex else f64,
                                    device=self.device)
         self.rewards = torch.zeros((T, N), dtype=f64, device=self.device)
@@ -87,24 +91,35 @@ def collect_rollouts(env, policy, n_steps, buffer=None, gamma=0.99, gae_lambda=0
     N, M = venv.num_envs, venv.M
     normalised = env is not venv and getattr(env, "norm_obs", False)
 
-    def current_obs():
-        return env.norm_planes[:, :N] if normalised else venv.S[:, :N]
-
     if buffer is None:
         buffer = RolloutBuffer(n_steps, N, 4 * M, venv._kernel_n_act or venv.n_act, venv.device, gamma, gae_lambda,
-                               action_is_complex=venv.free_action_space)
+                               action_is_complex=venv.free_action_space, ld=venv.ld)
     buffer.reset()
+    # normalised env + a buffer with the env's plane stride: the normalisation kernel writes the next observation
+    # straight into its buffer slot (no norm_planes -> buffer copy per step); only slot 0 is filled by a copy
+    direct = bool(normalised and buffer.ld == venv.ld and buffer.obs_store.dtype == venv.S.dtype and n_steps > 0)
+    if direct:
+        buffer.obs_store[0].copy_(env.current_norm_planes)
+
+    def current_obs():
+        return env.current_norm_planes[:, :N] if normalised else venv.S[:, :N]
+
     starts = getattr(env, "_last_episode_starts", None)
     if starts is None:
         starts = torch.ones(N, dtype=torch.uint8, device=venv.device)
     dones = starts
     for _ in range(n_steps):
-        obs = current_obs()
-        actions, values, log_probs = policy(obs)
-        buffer.observations[buffer.pos].copy_(obs)  # before the step overwrites the planes
-        out = env.step_tensor(actions if venv._kernel_n_act else None)
-        dones = (out["flags"] & _lib.FLAG_DONE).ne(0)
         t = buffer.pos
+        if direct:
+            obs = buffer.observations[t]
+            actions, values, log_probs = policy(obs)
+            nxt = buffer.obs_store[t + 1] if t + 1 < n_steps else env.norm_planes
+            out = env.step_tensor(actions if venv._kernel_n_act else None, obs_out=nxt)
+        else:
+            obs = current_obs()
+            actions, values, log_probs = policy(obs)
+            buffer.observations[t].copy_(obs)  # before the step overwrites the planes
+            out = env.step_tensor(actions if venv._kernel_n_act else None)
         buffer.actions[t].copy_(actions)
         buffer.rewards[t].copy_(out["reward"])
         buffer.episode_starts[t].copy_(starts)
@@ -113,7 +128,8 @@ def collect_rollouts(env, policy, n_steps, buffer=None, gamma=0.99, gae_lambda=0
         if log_probs is not None:
             buffer.log_probs[t].copy_(log_probs)
         buffer.pos += 1
-        starts = dones.to(torch.uint8)
+        starts = out["flags"] & _lib.FLAG_DONE  # uint8 0/1: the next step's episode_starts
+    dones = starts
     buffer.full = buffer.pos == buffer.n_steps
     env._last_episode_starts = starts
     _, last_values, _ = policy(current_obs())

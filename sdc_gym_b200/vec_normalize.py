@@ -50,6 +50,25 @@ class _RunningMeanStd:
         self.count2.fill_(float(st["count"]))
 
 
+class _StepOut(dict):
+    """Result dict of ``VecNormalize.step_tensor``: the normalised terminal planes are produced on first access
+    (SB3 normalises ``terminal_observation`` only for the envs that finished; a rollout loop that never looks at
+    them should not pay a 2 x 32M-byte pass per env-step for it).  Valid until the next step."""
+
+    def __init__(self, base, terminal_fn):
+        super().__init__(base)
+        self._terminal_fn = terminal_fn
+
+    def __missing__(self, key):
+        if key == "terminal" and self._terminal_fn is not None:
+            self["terminal"] = self._terminal_fn()
+            return dict.__getitem__(self, "terminal")
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or (key == "terminal" and self._terminal_fn is not None)
+
+
 class VecNormalize:
     def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0,
                  gamma=0.99, epsilon=1e-8, sync=True):
@@ -70,9 +89,12 @@ class VecNormalize:
         self.returns = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
         self.norm_planes = torch.zeros_like(venv.S)
         self.norm_terminal = torch.zeros_like(venv.S)
+        self.current_norm_planes = self.norm_planes  # where the normalised current observation lives (see step_tensor)
         self.norm_reward_buf = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
         nscr = self._L.sdcgym_vecnorm_scratch_doubles(self.P)
         self._scratch = torch.zeros(nscr, dtype=torch.float64, device=dev)
+        self._rscratch = torch.zeros(self._L.sdcgym_vecnorm_scratch_doubles(1), dtype=torch.float64, device=dev)
+        self.fused_update = True  # single-rank: accumulate + merge in one launch (False: the three-kernel sequence)
         self._sums = torch.zeros(2 * self.P + 1, dtype=torch.float64, device=dev)
         self._rsums = torch.zeros(3, dtype=torch.float64, device=dev)
         self._obs_aos = torch.zeros((max(N, 1), 2, M, 2), dtype=torch.float64, device=dev)
@@ -95,8 +117,17 @@ class VecNormalize:
         return self._global_n
 
     # ---- statistics --------------------------------------------------------------------------------
+    def _multi_rank(self):
+        return self.sync and _dist_mod.is_distributed()
+
     def _update(self, rms, planes_ptr, P, N, ld, sums):
         L, s = self._L, self._stream()
+        if self.fused_update and not self._multi_rank():
+            scratch = self._scratch if P > 1 else self._rscratch
+            _lib.check(L.sdcgym_vecnorm_update(P, N, ld, planes_ptr, rms.mean.data_ptr(), rms.var.data_ptr(),
+                                               rms.count2.data_ptr(), scratch.data_ptr(), sums.data_ptr(), s),
+                       "vecnorm_update")
+            return
         _lib.check(L.sdcgym_vecnorm_accumulate(P, N, ld, planes_ptr, rms.mean.data_ptr(), self._scratch.data_ptr(),
                                                sums.data_ptr(), s), "vecnorm_accumulate")
         total = float(N)
@@ -130,25 +161,47 @@ class VecNormalize:
             if self.training:
                 self._update(self.obs_rms, v.S.data_ptr(), self.P, v.num_envs, v.ld, self._sums)
             self._normalize_planes(v.S, self.norm_planes)
+            self.current_norm_planes = self.norm_planes
             return self._obs_out(self.norm_planes)
         return self._obs_out(v.S)
 
-    def step_tensor(self, actions=None):
+    def _normalized_terminal(self):
+        self._normalize_planes(self.venv.terminal, self.norm_terminal)
+        return self.norm_terminal[:, : self.venv.num_envs]
+
+    def step_tensor(self, actions=None, obs_out=None):
         """Device-resident normalised step.  Returns the env's dict plus ``obs_planes`` (normalised S planes),
-        ``reward`` replaced by the normalised reward and ``raw_reward``."""
+        ``reward`` replaced by the normalised reward and ``raw_reward``; ``terminal`` (normalised terminal planes)
+        is computed when first read.  ``obs_out``: optional (4M, ld) float64 CUDA tensor that receives the
+        normalised observation instead of ``self.norm_planes`` (a rollout buffer slot: saves one pass)."""
         v, L, s = self.venv, self._L, self._stream()
-        out = dict(v.step_tensor(actions))
+        raw = v.step_tensor(actions)
         N = v.num_envs
-        out["raw_reward"] = out["reward"]
         if self.norm_obs:
+            out = _StepOut(raw, self._normalized_terminal)
+            del out["terminal"]
             if self.training:
                 self._update(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
-            self._normalize_planes(v.S, self.norm_planes)
-            self._normalize_planes(v.terminal, self.norm_terminal)
-            out["obs_planes"], out["terminal"] = self.norm_planes[:, :N], self.norm_terminal[:, :N]
+            dst = self.norm_planes
+            if obs_out is not None:
+                if (obs_out.shape != v.S.shape or obs_out.dtype != v.S.dtype or not obs_out.is_contiguous()
+                        or obs_out.device != v.S.device):
+                    raise ValueError(f"obs_out must be a contiguous {tuple(v.S.shape)} float64 tensor on {v.S.device}")
+                dst = obs_out
+            self._normalize_planes(v.S, dst)
+            self.current_norm_planes = dst
+            out["obs_planes"] = dst[:, :N]
         else:
+            out = dict(raw)
             out["obs_planes"] = v.S[:, :N]
-        if self.training:
+        out["raw_reward"] = raw["reward"]
+        if self.training and self.fused_update and not self._multi_rank():
+            r = self.ret_rms
+            _lib.check(L.sdcgym_vecnorm_update_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(),
+                                                       r.mean.data_ptr(), r.var.data_ptr(), r.count2.data_ptr(),
+                                                       self._rscratch.data_ptr(), self._rsums.data_ptr(), s),
+                       "vecnorm_update_returns")
+        elif self.training:
             _lib.check(L.sdcgym_vecnorm_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(), s), "returns")
             self._update(self.ret_rms, self.returns.data_ptr(), 1, N, max(N, 1), self._rsums)
         _lib.check(L.sdcgym_vecnorm_reward(N, v.reward.data_ptr(), v.flags.data_ptr(), self.ret_rms.var.data_ptr(),
@@ -178,11 +231,16 @@ class VecNormalize:
         niter = out["niter"].cpu().numpy()
         lam = out["lam"].cpu().numpy()
         trunc = _TruncatedKey(niter, MAX_EPISODE_STEPS[v.envname])
-        term_planes = self.norm_terminal if self.norm_obs else v.terminal
         infos = LazyInfos(niter, out["residual"].cpu().numpy(), lam, dones, trunc,
-                          lambda: self._terminal_host(term_planes))
+                          lambda: self._terminal_host(self._terminal_planes_full()))
         infos.flags = flags
         return obs, out["reward"].cpu().numpy(), dones, infos
+
+    def _terminal_planes_full(self):
+        if not self.norm_obs:
+            return self.venv.terminal
+        self._normalize_planes(self.venv.terminal, self.norm_terminal)
+        return self.norm_terminal
 
     def _terminal_host(self, planes):
         t = self._obs_out(planes)

@@ -75,6 +75,32 @@ def test_vec_normalize_matches_sb3_semantics():
     assert abs(env2.obs_rms.count - env.obs_rms.count) < 1e-9  # not training: untouched
 
 
+def test_fused_statistics_update_is_bit_identical_to_the_three_kernel_sequence():
+    """single-rank fast path (sdcgym_vecnorm_update / _update_returns: accumulate + fold + merge in one launch) against
+    accumulate -> merge -> commit (the multi-rank sequence, with the all-reduce between the first two)"""
+    import torch
+    n = 5000  # ragged: not a multiple of the block size
+    x = torch.as_tensor(np.diag(fixed_preconditioner("min", 5)).copy(), device="cuda")
+    envs = []
+    for fused in (True, False):
+        e = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=9, reward_iteration_only=False,
+                                                        output="torch", **KW), gamma=0.95)
+        e.fused_update = fused
+        e.reset()
+        envs.append(e)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(4)
+    for s in range(20):
+        act = 2 * (x[None] + (torch.rand((n, 5), dtype=torch.float64, device="cuda", generator=gen) - 0.5) * 0.2) - 1
+        outs = [e.step_tensor(act) for e in envs]
+        for key in ("obs_planes", "reward", "raw_reward", "flags"):
+            assert torch.equal(outs[0][key], outs[1][key]), f"step {s} {key}"
+        for rms in ("obs_rms", "ret_rms"):
+            a, b = getattr(envs[0], rms), getattr(envs[1], rms)
+            assert torch.equal(a.mean, b.mean) and torch.equal(a.var, b.var) and a.count == b.count, f"step {s} {rms}"
+        assert torch.equal(envs[0].returns, envs[1].returns)
+    assert envs[0].obs_rms.count == pytest.approx(1e-4 + 21 * n)
+
+
 def test_env_state_dict_round_trip():
     n = 1000
     a = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=4, **KW)
@@ -185,6 +211,29 @@ def test_gae_kernel_and_rollout_collection():
     assert torch.allclose(b.values, b.observations[:, 0] * 0.1)
     b2 = collect_rollouts(env, policy, 24, buffer=b)  # continues the episodes
     assert b2 is b and not bool(b.episode_starts[0].all())
+    # the normalisation kernel writes straight into the buffer slots (`obs_out`); a buffer with another plane
+    # stride takes the copying path: both must collect identical rollouts, twice in a row
+    from sdc_gym_b200.rollout import RolloutBuffer
+    runs = []
+    for ld in (None, n + 64):
+        e = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=3, output="torch", **KW))
+        e.reset()
+        gen.manual_seed(5)
+        buf = None if ld is None else RolloutBuffer(12, n, 20, 5, "cuda", ld=ld)
+        buf = collect_rollouts(e, policy, 12, buffer=buf)
+        first = [t.clone() for t in (buf.observations, buf.rewards, buf.advantages, buf.episode_starts)]
+        buf = collect_rollouts(e, policy, 12, buffer=buf)
+        runs.append(first + [t.clone() for t in (buf.observations, buf.rewards, buf.advantages, buf.episode_starts)])
+    assert runs[0][0].data_ptr() != runs[1][0].data_ptr()
+    for a, c in zip(*runs):
+        assert torch.equal(a, c)
+    # the normalised terminal planes are produced on demand
+    out = e.step_tensor(policy(e.current_norm_planes[:, :n])[0])
+    assert "terminal" in out and not dict.__contains__(out, "terminal")
+    term = out["terminal"]
+    mean, var = e.obs_rms.mean, e.obs_rms.var
+    ref_t = ((e.venv.terminal[:, :n] - mean[:, None]) / torch.sqrt(var[:, None] + e.epsilon)).clamp(-10, 10)
+    assert torch.allclose(term, ref_t, rtol=1e-13, atol=1e-13) and dict.__contains__(out, "terminal")
 
 
 def test_spectral_radius_value_and_grad_and_autograd():
