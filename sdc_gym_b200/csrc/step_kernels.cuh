@@ -47,6 +47,7 @@ struct StepParams {
     uint64_t seed;
     int64_t env_offset;
     int32_t prec_type, is_complex, do_scale, max_iters, strategy, autoreset, curriculum;
+    double log_restol_nf;  // math.log(restol * norm_factor) (sdc_env.py:346), evaluated once on the host
 };
 
 // ---- C = eye(M) - (lam*dt)*Q, one row (sdc_env.py:302-304; Appendix A step 2).  0 - x is written -x
@@ -179,19 +180,22 @@ SDCGYM_HD double scaled_inf_norm(const double (&vr)[M], const double (&vi)[M], d
         tr[m] = dmul(vr[m], nf);  // numpy complex * real scalar
         ti[m] = dmul(vi[m], nf);
     }
-    return inf_norm<M>(tr, ti);
+    // same value as inf_norm (abs(v).max()): numpy's |.| is evaluated only for the node that provably attains the
+    // maximum (one division + square root instead of M of them)
+    return inf_norm_fast<M>(tr, ti);
 }
 
 template <int M>
 SDCGYM_HD_NOINLINE double reward_func(int strategy, double sp, double rw, double nf, double restol, int max_iters,
                                            double norm_old_scaled, double norm_init_scaled, const double (&rr)[M],
-                                           const double (&ri)[M], double nr, bool converged, int steps) {
+                                           const double (&ri)[M], double nr, bool converged, int steps,
+                                           double log_restol_nf) {
     switch (strategy) {
     case SDCGYM_REW_ITERATION_ONLY:
         return dmul((double)(-steps), sp);
     case SDCGYM_REW_RESIDUAL_CHANGE: {
         double b = (nf == 1.0) ? nr : scaled_inf_norm<M>(rr, ri, nf);
-        double rew = fabs(ddiv(dsub(log(norm_old_scaled), log(b)), dsub(log(norm_init_scaled), log(dmul(restol, nf)))));
+        double rew = fabs(ddiv(dsub(log(norm_old_scaled), log(b)), dsub(log(norm_init_scaled), log_restol_nf)));
         rew = dmul(rew, rw);
         rew = dsub(rew, dmul((double)steps, sp));
         return rew;
@@ -636,7 +640,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             if (KIND == SDCGYM_ENV_FULL) norm_old_scaled = norm_init_scaled;  // reward_func(initial_residual, ...)
         }
         rew = reward_func<M>(p.strategy, p.step_penalty, p.residual_weight, p.norm_factor, p.restol, p.max_iters,
-                             norm_old_scaled, norm_init_scaled, rr, ri, nr, conv, it);
+                             norm_old_scaled, norm_init_scaled, rr, ri, nr, conv, it, p.log_restol_nf);
     }
 
     const bool done = (KIND == SDCGYM_ENV_FULL) ? true : (conv || it >= p.max_iters || err);

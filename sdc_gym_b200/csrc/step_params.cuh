@@ -49,6 +49,7 @@ inline void fill_params(StepParams<M>& p, const sdcgym_env_desc* d, const sdcgym
     p.strategy = d->reward_strategy;
     p.autoreset = d->autoreset;
     p.curriculum = d->curriculum;
+    p.log_restol_nf = log(d->restol * d->norm_factor);
 }
 
 

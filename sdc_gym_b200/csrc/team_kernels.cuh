@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
             ti[m] = Ri[m];
         }
         rew = reward_func<M>(p.strategy, p.step_penalty, p.residual_weight, p.norm_factor, p.restol, p.max_iters,
-                             norm_old_scaled, norm_init_scaled, tr, ti, nr, conv, it);
+                             norm_old_scaled, norm_init_scaled, tr, ti, nr, conv, it, p.log_restol_nf);
     }
     const bool done = (KIND == SDCGYM_ENV_FULL) ? true : (conv || it >= p.max_iters || err);
 

