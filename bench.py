@@ -325,7 +325,7 @@ def run_ours(args):
                          "note": "bit-exact emulation of the reference's rounding sequence needs 183 FP64 instructions "
                                  "(mul/add/fma, <= 1 FMA each) per 210-flop sweep: instruction-level ceiling of the "
                                  "algorithmic fraction = 210/(2*183) = 0.57, x 0.87 lane efficiency (envs of a warp stop "
-                                 "at different sweeps) = 0.49; FP64 pipe measured 73 % busy (profiles/)",
+                                 "at different sweeps) = 0.49; measured (ncu, profiles/ncu_step_kernel_r01_shipped_summary.json): FP64 pipe 76 % busy, shared-memory/LSU data pipe 81 % (25 LDS.128 of C per sweep) - the two co-limit the kernel",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_achieved / hbm_peak, "bytes_per_env_step": BYTES_PER_ENV_STEP_V0,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}},
