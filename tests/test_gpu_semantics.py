@@ -355,6 +355,27 @@ def test_use_doubles_false_action_space_and_parity():
     assert envc.action_space.dtype == np.complex64
 
 
+def test_zero_residual_reward_is_nan_where_the_reference_raises():
+    """lambda = 0: C = I, r0 = 0 exactly; `math.log(0)` raises ValueError in the reference's residual_change reward
+    (sdc_env.py:337-350) - documented deviation: NaN for that env; fast_convergence returns 1000 (:380)."""
+    n = 64
+    lam = np.zeros(n, np.complex128)
+    lam[1::2] = -1.0 - 0.5j
+    act = np.zeros((n, 5))
+    for strategy, want in (("residual_change", np.nan), ("fast_convergence", 1000.0)):
+        env = sdc_gym_b200.make("sdc-v1", num_envs=n, reward_iteration_only=None, reward_strategy=strategy,
+                                autoreset=False, **KW)
+        obs = env.reset(lam=lam)
+        assert np.all(obs[0::2, 1] == 0)
+        _, rew, done, infos = env.step(act)
+        assert np.all(infos.residual[0::2] == 0.0) and np.all(np.isfinite(rew[1::2]))
+        if np.isnan(want):
+            assert np.all(np.isnan(rew[0::2]))
+        else:
+            # converged at step 1: bonus (51 - 1)^2 * 10 on top of the zero-norm reward 1000 (sdc_env.py:370-385)
+            assert np.all(rew[0::2] == want * (50.0 ** 2) * 10.0)
+
+
 def test_spectral_radius_reward_strategy():
     n, M = 500, 5
     rng = np.random.default_rng(12)
