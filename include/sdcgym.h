@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 2
+#define SDCGYM_ABI_VERSION 3 /* 3: SDCGYM_ACTION_* bits in do_scale, sdcgym_vecnorm_update[_returns], scratch + 2 */
 #define SDCGYM_MAX_M 9
 
 /* error codes (negative); positive return values are cudaError_t */
