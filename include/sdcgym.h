@@ -261,6 +261,34 @@ int sdcgym_pipe_create(int max_chunks, sdcgym_pipe** out);
 int sdcgym_pipe_destroy(sdcgym_pipe* pipe);
 int sdcgym_pipe_step(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* dev,
                      double* obs_dev, const sdcgym_host_io* host, int chunks, void* caller_stream);
+/*
+ * The same host-buffer step through a device-side VecNormalize (utils/utils.py:295-312: DummyVecEnv wrapped in
+ * VecNormalize is how the reference trains): step -> statistics update (training) -> normalised observation planes
+ * -> discounted returns / return statistics -> normalised reward -> host, in one call and, for small batches, one
+ * D2H transfer.  `host->obs` and `host->reward` receive the NORMALISED observation / reward; the raw reward stays
+ * in `dev->reward`.  Single-rank statistics only (a multi-rank normaliser needs the all-reduce between
+ * sdcgym_vecnorm_accumulate and _merge).  All pointers are device memory owned by the caller.
+ */
+typedef struct sdcgym_vecnorm {
+    int32_t norm_obs, norm_reward, training, reserved;
+    double gamma, epsilon, clip_obs, clip_reward;
+    double* obs_mean;    /* [4M] */
+    double* obs_var;     /* [4M] */
+    double* obs_count2;  /* [2] */
+    double* ret_mean;    /* [1] */
+    double* ret_var;     /* [1] */
+    double* ret_count2;  /* [2] */
+    double* returns;     /* [N] discounted returns */
+    double* scratch_obs; /* sdcgym_vecnorm_scratch_doubles(4M), zero-initialised once */
+    double* scratch_ret; /* sdcgym_vecnorm_scratch_doubles(1), zero-initialised once */
+    double* sums_obs;    /* [2*4M + 1] */
+    double* sums_ret;    /* [3] */
+    double* out_planes;  /* [4M][ld] normalised observation planes (output) */
+    double* out_reward;  /* [N] normalised reward (output; the raw reward if !norm_reward) */
+} sdcgym_vecnorm;
+int sdcgym_pipe_step_vecnorm(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgym_state* st,
+                             const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host,
+                             const sdcgym_vecnorm* vn, void* caller_stream);
 int sdcgym_host_alloc(size_t bytes, void** out); /* page-locked host memory */
 int sdcgym_host_free(void* p);
 

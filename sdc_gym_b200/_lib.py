@@ -130,6 +130,22 @@ class HostIO(ctypes.Structure):
     ]
 
 
+class VecNorm(ctypes.Structure):
+    """struct sdcgym_vecnorm"""
+
+    _fields_ = [
+        ("norm_obs", ctypes.c_int32), ("norm_reward", ctypes.c_int32), ("training", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("gamma", ctypes.c_double), ("epsilon", ctypes.c_double), ("clip_obs", ctypes.c_double),
+        ("clip_reward", ctypes.c_double),
+        ("obs_mean", ctypes.c_void_p), ("obs_var", ctypes.c_void_p), ("obs_count2", ctypes.c_void_p),
+        ("ret_mean", ctypes.c_void_p), ("ret_var", ctypes.c_void_p), ("ret_count2", ctypes.c_void_p),
+        ("returns", ctypes.c_void_p), ("scratch_obs", ctypes.c_void_p), ("scratch_ret", ctypes.c_void_p),
+        ("sums_obs", ctypes.c_void_p), ("sums_ret", ctypes.c_void_p), ("out_planes", ctypes.c_void_p),
+        ("out_reward", ctypes.c_void_p),
+    ]
+
+
 class SdcGymError(RuntimeError):
     pass
 
@@ -183,9 +199,12 @@ def load():
     L.sdcgym_pipe_destroy.argtypes = [vp]
     L.sdcgym_pipe_step.argtypes = [vp, ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(StepIO), vp,
                                    ctypes.POINTER(HostIO), ctypes.c_int, vp]
+    L.sdcgym_pipe_step_vecnorm.argtypes = [vp, ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(StepIO), vp,
+                                           ctypes.POINTER(HostIO), ctypes.POINTER(VecNorm), vp]
     L.sdcgym_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.sdcgym_host_free.argtypes = [vp]
-    for name in ("sdcgym_pipe_create", "sdcgym_pipe_destroy", "sdcgym_pipe_step", "sdcgym_host_alloc", "sdcgym_host_free"):
+    for name in ("sdcgym_pipe_create", "sdcgym_pipe_destroy", "sdcgym_pipe_step", "sdcgym_pipe_step_vecnorm",
+                 "sdcgym_host_alloc", "sdcgym_host_free"):
         getattr(L, name).restype = ctypes.c_int
     L.sdcgym_gae.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     L.sdcgym_gae.restype = ctypes.c_int

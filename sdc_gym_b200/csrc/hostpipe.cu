@@ -130,9 +130,55 @@ static int64_t chunk_begin(int64_t N, int c, int chunks) {
     return (int64_t)((double)N * f * sqrt(f)) / 32 * 32;
 }
 
+// device-side VecNormalize between the step and the download (single stream, in order)
+static int run_vecnorm(const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* dev,
+                       const sdcgym_vecnorm* vn, cudaStream_t cs) {
+    const int P = 4 * desc->M;
+    const int64_t N = st->N;
+    int rc = 0;
+    if (vn->norm_obs) {
+        if (vn->training) {
+            rc = sdcgym_vecnorm_update(P, N, st->ld, st->S, vn->obs_mean, vn->obs_var, vn->obs_count2, vn->scratch_obs,
+                                       vn->sums_obs, cs);
+            if (rc) return rc;
+        }
+        rc = sdcgym_vecnorm_apply(P, N, st->ld, st->S, vn->obs_mean, vn->obs_var, vn->epsilon, vn->clip_obs,
+                                  vn->out_planes, cs);
+        if (rc) return rc;
+    }
+    if (vn->training) {
+        rc = sdcgym_vecnorm_update_returns(N, dev->reward, vn->gamma, vn->returns, vn->ret_mean, vn->ret_var,
+                                           vn->ret_count2, vn->scratch_ret, vn->sums_ret, cs);
+        if (rc) return rc;
+    }
+    return sdcgym_vecnorm_reward(N, dev->reward, dev->flags, vn->ret_var, vn->epsilon, vn->clip_reward, vn->norm_reward ? 1 : 0,
+                                 vn->out_reward, vn->returns, cs);
+}
+
+static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* dev,
+                          double* obs_dev, const sdcgym_host_io* host, int chunks, const sdcgym_vecnorm* vn,
+                          void* caller_stream);
+
 extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st,
                                 const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host, int chunks,
                                 void* caller_stream) {
+    return pipe_step_impl(p, desc, st, dev, obs_dev, host, chunks, nullptr, caller_stream);
+}
+
+extern "C" int sdcgym_pipe_step_vecnorm(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st,
+                                        const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host,
+                                        const sdcgym_vecnorm* vn, void* caller_stream) {
+    if (!vn) return SDCGYM_ENULL;
+    if (!dev || !dev->reward || !dev->flags || !vn->out_reward || !vn->returns || !vn->ret_var) return SDCGYM_ENULL;
+    if (vn->norm_obs && (!vn->out_planes || !vn->obs_mean || !vn->obs_var)) return SDCGYM_ENULL;
+    if (vn->training && (!vn->ret_mean || !vn->ret_count2 || !vn->scratch_ret || !vn->sums_ret)) return SDCGYM_ENULL;
+    if (vn->training && vn->norm_obs && (!vn->obs_count2 || !vn->scratch_obs || !vn->sums_obs)) return SDCGYM_ENULL;
+    return pipe_step_impl(p, desc, st, dev, obs_dev, host, 1, vn, caller_stream);
+}
+
+static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgym_step_io* dev,
+                          double* obs_dev, const sdcgym_host_io* host, int chunks, const sdcgym_vecnorm* vn,
+                          void* caller_stream) {
     if (!p || !desc || !st || !dev || !host) return SDCGYM_ENULL;
     const int64_t N = st->N;
     if (N < 0 || chunks < 1) return SDCGYM_EINVAL;
@@ -159,8 +205,16 @@ extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, con
         }
         int rc = sdcgym_step(desc, st, &io, cs);
         if (rc) return rc;
+        const double* obs_src = st->S;
+        const double* rew_src = dev->reward;
+        if (vn) {
+            rc = run_vecnorm(desc, st, dev, vn, cs);
+            if (rc) return rc;
+            if (vn->norm_obs) obs_src = vn->out_planes;
+            rew_src = vn->out_reward;
+        }
         pack_results_kernel<<<(unsigned)((N + 127) / 128), 128, 0, cs>>>(
-            M, N, st->ld, st->S, host->reward ? dev->reward : nullptr, host->residual ? dev->info_residual : nullptr,
+            M, N, st->ld, obs_src, host->reward ? rew_src : nullptr, host->residual ? dev->info_residual : nullptr,
             host->lam ? dev->info_lam : nullptr, host->niter ? dev->info_niter : nullptr,
             host->flags ? dev->flags : nullptr, p->pack_dev, L);
         PIPE_CHECK(cudaGetLastError());
@@ -177,6 +231,36 @@ extern "C" int sdcgym_pipe_step(sdcgym_pipe* p, const sdcgym_env_desc* desc, con
         return 0;
     }
 
+    if (vn) {
+        // normalised large batch: the statistics need the whole batch before any observation can leave, so the
+        // chunked overlap does not apply; one pass on the caller's stream (large-batch callers that care about
+        // throughput keep observations on the device: VecNormalize.step_tensor / collect_rollouts)
+        double* act_dev = const_cast<double*>(dev->action);
+        sdcgym_step_io io = *dev;
+        if (A > 0) {
+            PIPE_CHECK(cudaMemcpyAsync(act_dev, host->action, sizeof(double) * N * aw, cudaMemcpyHostToDevice, cs));
+            io.action_env_stride = aw;
+            io.action_comp_stride = desc->action_is_complex ? 2 : 1;
+        } else {
+            io.action = nullptr;
+        }
+        int rc = sdcgym_step(desc, st, &io, cs);
+        if (rc) return rc;
+        rc = run_vecnorm(desc, st, dev, vn, cs);
+        if (rc) return rc;
+        if (host->obs) {
+            rc = sdcgym_export_obs(M, N, st->ld, vn->norm_obs ? vn->out_planes : st->S, obs_dev, cs);
+            if (rc) return rc;
+            PIPE_CHECK(cudaMemcpyAsync(host->obs, obs_dev, (size_t)N * 4 * M * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        }
+        if (host->reward) PIPE_CHECK(cudaMemcpyAsync(host->reward, vn->out_reward, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (host->flags) PIPE_CHECK(cudaMemcpyAsync(host->flags, dev->flags, (size_t)N, cudaMemcpyDeviceToHost, cs));
+        if (host->niter && dev->info_niter) PIPE_CHECK(cudaMemcpyAsync(host->niter, dev->info_niter, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+        if (host->residual && dev->info_residual) PIPE_CHECK(cudaMemcpyAsync(host->residual, dev->info_residual, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        if (host->lam && dev->info_lam) PIPE_CHECK(cudaMemcpyAsync(host->lam, dev->info_lam, (size_t)N * 2 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        PIPE_CHECK(cudaStreamSynchronize(cs));
+        return 0;
+    }
     // everything the caller enqueued before this call happens before the pipeline starts
     PIPE_CHECK(cudaEventRecord(p->ev_start, cs));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));

@@ -601,22 +601,7 @@ class SDCVecEnv:
         chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(8, N // 131072))
         if self.host_pipeline == "native":
             # ---- one C call: chunked H2D | kernels | D2H pipeline inside libsdcgym.so (csrc/hostpipe.cu) ----
-            if self._pipe is None:
-                handle = ctypes.c_void_p()
-                _lib.check(self._L.sdcgym_pipe_create(64, ctypes.byref(handle)), "sdcgym_pipe_create")
-                self._pipe = handle
-            if self._pipe_args is None:
-                # the device / pinned buffers never move: build the argument structs once
-                io = _lib.StepIO()
-                io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
-                io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
-                io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
-                io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
-                hio = _lib.HostIO()
-                hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
-                hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
-                self._pipe_args = (io, hio, self._state(), self.obs_aos.data_ptr())
-            io, hio, st, obs_dev = self._pipe_args
+            io, hio, st, obs_dev = self._pipe_handles(host)
             hio.action = src.data_ptr() if src is not None else None
             _lib.check(self._L.sdcgym_pipe_step(self._pipe, ctypes.byref(self._desc), ctypes.byref(st), ctypes.byref(io),
                                                 obs_dev, ctypes.byref(hio), chunks, self._stream()),
@@ -654,6 +639,25 @@ class SDCVecEnv:
         main.wait_stream(s_out)
         self._invalidate()
         return self._host_outputs(host)
+
+    def _pipe_handles(self, host):
+        """The native host pipeline (csrc/hostpipe.cu) and its cached argument structs (io, hio, state, obs_dev)."""
+        if self._pipe is None:
+            handle = ctypes.c_void_p()
+            _lib.check(self._L.sdcgym_pipe_create(64, ctypes.byref(handle)), "sdcgym_pipe_create")
+            self._pipe = handle
+        if self._pipe_args is None:
+            # the device / pinned buffers never move: build the argument structs once
+            io = _lib.StepIO()
+            io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
+            io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
+            io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
+            io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
+            hio = _lib.HostIO()
+            hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
+            hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
+            self._pipe_args = (io, hio, self._state(), self.obs_aos.data_ptr())
+        return self._pipe_args
 
     def _step_simple(self, actions):
         """Unpipelined host step (rarely used configurations): upload, device step, download."""

@@ -210,11 +210,52 @@ class VecNormalize:
         out["reward"] = self.norm_reward_buf[:N]
         return out
 
+    def _vecnorm_struct(self):
+        vn = getattr(self, "_vn_struct", None)
+        if vn is None:
+            vn = _lib.VecNorm()
+            o, r = self.obs_rms, self.ret_rms
+            vn.obs_mean, vn.obs_var, vn.obs_count2 = o.mean.data_ptr(), o.var.data_ptr(), o.count2.data_ptr()
+            vn.ret_mean, vn.ret_var, vn.ret_count2 = r.mean.data_ptr(), r.var.data_ptr(), r.count2.data_ptr()
+            vn.returns = self.returns.data_ptr()
+            vn.scratch_obs, vn.scratch_ret = self._scratch.data_ptr(), self._rscratch.data_ptr()
+            vn.sums_obs, vn.sums_ret = self._sums.data_ptr(), self._rsums.data_ptr()
+            vn.out_planes, vn.out_reward = self.norm_planes.data_ptr(), self.norm_reward_buf.data_ptr()
+            self._vn_struct = vn
+        vn.norm_obs, vn.norm_reward, vn.training = int(self.norm_obs), int(self.norm_reward), int(self.training)
+        vn.gamma, vn.epsilon = float(self.gamma), float(self.epsilon)
+        vn.clip_obs, vn.clip_reward = float(self.clip_obs), float(self.clip_reward)
+        return vn
+
+    def _native_host_step(self, actions):
+        """numpy in / numpy out through ONE C call (``sdcgym_pipe_step_vecnorm``): upload, step, statistics,
+        normalisation, packed download - the reference's training regime (8 envs behind VecNormalize) is pure
+        latency, and the call-by-call path costs ~200 us per step against ~50 us here."""
+        v = self.venv
+        host = v._ensure_host()
+        src = v._stage_actions(host, actions) if v._kernel_n_act > 0 else None
+        io, hio, st, obs_dev = v._pipe_handles(host)
+        hio.action = src.data_ptr() if src is not None else None
+        vn = self._vecnorm_struct()
+        _lib.check(self._L.sdcgym_pipe_step_vecnorm(v._pipe, ctypes.byref(v._desc), ctypes.byref(st), ctypes.byref(io),
+                                                    obs_dev, ctypes.byref(hio), ctypes.byref(vn), v._stream()),
+                   "sdcgym_pipe_step_vecnorm")
+        v._invalidate()
+        if self.norm_obs:
+            self.current_norm_planes = self.norm_planes
+        self.old_reward = v.reward[: v.num_envs]
+        obs, rewards, dones, infos = v._host_outputs(host)
+        infos._terminal_fetch = lambda: self._terminal_host(self._terminal_planes_full())
+        return obs, rewards, dones, infos
+
     def step(self, actions):
         """(obs, rewards, dones, infos) with normalised obs / rewards (numpy or torch per the env's ``output``)."""
         torch = _torch()
         v = self.venv
         a = actions
+        if (v.output != "torch" and not (isinstance(a, torch.Tensor) and a.is_cuda) and v.host_pipeline == "native"
+                and self.fused_update and not self._multi_rank() and not v._rho_reward):
+            return self._native_host_step(a)
         if v._kernel_n_act > 0 and not (isinstance(a, torch.Tensor) and a.is_cuda):
             arr = np.asarray(a, dtype=np.complex128 if v.free_action_space else np.float64).reshape(v.num_envs, -1)
             a = torch.as_tensor(arr).to(v.device)

@@ -101,6 +101,43 @@ def test_fused_statistics_update_is_bit_identical_to_the_three_kernel_sequence()
     assert envs[0].obs_rms.count == pytest.approx(1e-4 + 21 * n)
 
 
+@pytest.mark.parametrize("n", [8, 1000, 5000])
+def test_native_normalised_host_step_equals_the_call_by_call_path(n):
+    """VecNormalize.step(numpy) through sdcgym_pipe_step_vecnorm (one C call; packed single transfer for small
+    batches, n = 8 / 1000; unpipelined large path, n = 5000) against the Python-driven sequence of the same kernels."""
+    rng = np.random.default_rng(n)
+    x = np.diag(fixed_preconditioner("min", 5))
+    envs = []
+    for native in (True, False):
+        e = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=11, reward_iteration_only=False, **KW),
+                                      gamma=0.9)
+        e.fused_update = native  # False: step() takes the call-by-call path (three-kernel statistics)
+        envs.append(e)
+    o0, o1 = envs[0].reset(), envs[1].reset()
+    assert np.array_equal(o0, o1)
+    saw_done = False
+    for s in range(60):
+        act = 2 * (x[None] + rng.uniform(-0.05, 0.05, (n, 5))) - 1
+        (oa, ra, da, ia), (ob, rb, db, ib) = envs[0].step(act), envs[1].step(act)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db), f"step {s}"
+        assert np.array_equal(ia.niter, ib.niter) and np.array_equal(ia.residual, ib.residual)
+        assert np.array_equal(ia.lam, ib.lam) and np.array_equal(ia.flags, ib.flags)
+        assert np.array_equal(envs[0].get_original_reward(), envs[1].get_original_reward())
+        if da.any():
+            saw_done = True
+            k = int(np.nonzero(da)[0][0])
+            assert np.array_equal(ia[k]["terminal_observation"], ib[k]["terminal_observation"])
+    assert saw_done
+    assert envs[0].obs_rms.count == envs[1].obs_rms.count
+    # evaluation mode: statistics frozen
+    for e in envs:
+        e.training = False
+    cnt = envs[0].obs_rms.count
+    act = 2 * (x[None] + rng.uniform(-0.05, 0.05, (n, 5))) - 1
+    (oa, ra, _, _), (ob, rb, _, _) = envs[0].step(act), envs[1].step(act)
+    assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and envs[0].obs_rms.count == cnt
+
+
 def test_env_state_dict_round_trip():
     n = 1000
     a = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=4, **KW)
