@@ -17,6 +17,10 @@
 #pragma once
 #include "exact_math.cuh"
 
+#ifndef SDCGYM_QR_HOOK
+#define SDCGYM_QR_HOOK(hi)  // experiment hook (tools/qr_iteration_count.cpp): one QR step on the leading (hi+1) block
+#endif
+
 namespace sdcgym {
 
 struct C2 {
@@ -147,6 +151,7 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M], C2* mu_out = nullptr) {
             mu = (c_abs2(den) == 0.0) ? d1 : c_sub(d1, c_div(bc, den));
         }
         its++;
+        SDCGYM_QR_HOOK(hi);
 #pragma unroll
         for (int k = 0; k < M; k++)
             if (k <= hi) H_(k, k) = c_sub(H_(k, k), mu);
