@@ -114,6 +114,42 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M], C2* mu_out = nullptr) {
         }
     }
 
+    // ---- is the matrix numerically singular?  A well-trained Q_delta makes Q - Qd (nearly) singular (MIN: one
+    //      eigenvalue ~1e-10 next to a cluster of three around 0.2), and then ONE unshifted step deflates the null
+    //      eigenvalue at once and the remaining, hard cluster is iterated on a smaller block: 13 instead of 21 QR steps
+    //      on the MIN grid (profiles/README.md).  |det H| by Hyman's recurrence on the Hessenberg form (~2 % of the
+    //      work) against the scale (||H||_F^2 / M)^(M/2); any other matrix takes the Wilkinson shift from the start. ----
+    bool zero_first = false;
+    if (M >= 3) {
+        C2 xh[M];
+        xh[M - 1] = C2{1.0, 0.0};
+        bool ok = true;
+        double prod2 = 1.0;
+#pragma unroll
+        for (int i = M - 1; i >= 1; i--) {
+            C2 s{0.0, 0.0};
+#pragma unroll
+            for (int j = i; j < M; j++) s = c_add(s, c_mul(H_(i, j), xh[j]));
+            const C2 sub = H_(i, i - 1);
+            const double a2 = c_abs2(sub);
+            ok = ok && (a2 > 1e-60) && (a2 < 1e60);
+            prod2 *= a2;
+            const double ia2 = ok ? -1.0 / a2 : 0.0;  // x_{i-1} = -s / sub = -s conj(sub) / |sub|^2
+            xh[i - 1] = c_scale(c_mul(s, c_conj(sub)), ia2);
+        }
+        C2 top{0.0, 0.0};
+        double fro2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; j++) top = c_add(top, c_mul(H_(0, j), xh[j]));
+#pragma unroll
+        for (int k = 0; k < M * M; k++) fro2 += c_abs2(H[k]);
+        double scale2 = 1.0;  // (fro2 / M)^M = scale^2
+#pragma unroll
+        for (int k = 0; k < M; k++) scale2 *= fro2 * (1.0 / M);
+        const double det2 = c_abs2(top) * prod2;
+        zero_first = ok && (det2 <= 1e-12 * scale2) && (scale2 > 0.0) && (scale2 < 1e300);
+    }
+
     // ---- shifted QR on the Hessenberg matrix, deflating from the bottom ----
     const double eps = 2.220446049250313e-16;
     double rho = 0.0;
@@ -147,7 +183,10 @@ SDCGYM_HD double max_abs_eig(C2 (&H)[M * M], C2* mu_out = nullptr) {
         }
         // Wilkinson shift: eigenvalue of [[d0, b01], [sub, d1]] closer to d1
         C2 mu;
-        if (its == 10 || its == 20) {
+        if (zero_first) {
+            mu = C2{0.0, 0.0};
+            zero_first = false;
+        } else if (its == 10 || its == 20) {
             mu = C2{d1.r + fabs(sub.r) + fabs(sub.i), d1.i};  // exceptional shift
         } else {
             C2 half = c_scale(c_sub(d0, d1), 0.5);
