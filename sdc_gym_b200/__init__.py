@@ -67,9 +67,12 @@ def make_env(args, num_envs=None, include_norm=False, norm_reward=True, **kwargs
     env = make(args.envname, num_envs=num_envs, seed=seed, **all_kwargs)
     if include_norm:
         from .vec_normalize import VecNormalize
-        model_kwargs = getattr(args, "model_kwargs", None) or {}
-        extra = {"gamma": model_kwargs["gamma"]} if "gamma" in model_kwargs else {}
-        env = VecNormalize(env, norm_obs=getattr(args, "norm_obs", True), norm_reward=norm_reward, **extra)
+        if getattr(args, "env_path", None) is not None:  # utils/utils.py:296-297: resume a saved normaliser
+            env = VecNormalize.load(str(args.env_path), env)
+        else:
+            model_kwargs = getattr(args, "model_kwargs", None) or {}
+            extra = {"gamma": model_kwargs["gamma"]} if "gamma" in model_kwargs else {}
+            env = VecNormalize(env, norm_obs=getattr(args, "norm_obs", True), norm_reward=norm_reward, **extra)
     if getattr(args, "debug_nans", False):
         from .vec_normalize import VecCheckNan
         env = VecCheckNan(env, raise_exception=True)

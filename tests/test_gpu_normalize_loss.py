@@ -205,6 +205,20 @@ def test_make_env_mirrors_reference_factory_and_check_nan():
     action = [np.empty(env2.action_space.shape, dtype=env2.action_space.dtype) for _ in range(8)]
     o, r, d, i = env2.step(action)
     assert o.shape == (8, 2, 5)
+    # SAC: float32 action space (utils/utils.py:279-280); env_path: the saved normaliser is resumed (:296-297)
+    args.model_class, args.debug_nans = "SAC", False
+    env3 = sdc_gym_b200.make_env(args, include_norm=True)
+    assert env3.action_space.dtype == np.float32
+    env3.reset()
+    for _ in range(3):
+        env3.step(np.zeros((64, 3), np.float32))
+    import tempfile, os as _os
+    path = _os.path.join(tempfile.mkdtemp(), "vecnormalize.pkl")
+    env3.save(path)
+    args.env_path = path
+    env4 = sdc_gym_b200.make_env(args, include_norm=True)
+    assert env4.obs_rms.count == env3.obs_rms.count
+    assert np.array_equal(env4.obs_rms.mean.cpu().numpy(), env3.obs_rms.mean.cpu().numpy())
 
 
 def test_gae_kernel_and_rollout_collection():
