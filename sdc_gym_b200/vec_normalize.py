@@ -95,8 +95,11 @@ class VecNormalize:
         self._scratch = torch.zeros(nscr, dtype=torch.float64, device=dev)
         self._rscratch = torch.zeros(self._L.sdcgym_vecnorm_scratch_doubles(1), dtype=torch.float64, device=dev)
         self.fused_update = True  # single-rank: accumulate + merge in one launch (False: the three-kernel sequence)
-        self._sums = torch.zeros(2 * self.P + 1, dtype=torch.float64, device=dev)
-        self._rsums = torch.zeros(3, dtype=torch.float64, device=dev)
+        # shifted sums of the observation planes and of the returns, contiguous so that a multi-rank step needs ONE
+        # all-reduce for both statistics
+        self._allsums = torch.zeros(2 * self.P + 1 + 3, dtype=torch.float64, device=dev)
+        self._sums = self._allsums[: 2 * self.P + 1]
+        self._rsums = self._allsums[2 * self.P + 1:]
         self._obs_aos = torch.zeros((max(N, 1), 2, M, 2), dtype=torch.float64, device=dev)
         self.old_reward = None
 
@@ -128,14 +131,20 @@ class VecNormalize:
                                                rms.count2.data_ptr(), scratch.data_ptr(), sums.data_ptr(), s),
                        "vecnorm_update")
             return
-        _lib.check(L.sdcgym_vecnorm_accumulate(P, N, ld, planes_ptr, rms.mean.data_ptr(), self._scratch.data_ptr(),
-                                               sums.data_ptr(), s), "vecnorm_accumulate")
+        self._accumulate(rms, planes_ptr, P, N, ld, sums)
         total = float(N)
         if self.sync and _dist_mod.is_distributed():
-            _dist_mod.all_reduce_sum(sums)  # < 1 kB, latency bound; the only collective of a normalised step
+            _dist_mod.all_reduce_sum(sums)  # < 1 kB, latency bound
             total = self._global_count(N)
-        _lib.check(L.sdcgym_vecnorm_merge(P, total, sums.data_ptr(), rms.mean.data_ptr(), rms.var.data_ptr(),
-                                          rms.count2.data_ptr(), s), "vecnorm_merge")
+        self._merge(rms, P, total, sums)
+
+    def _accumulate(self, rms, planes_ptr, P, N, ld, sums):
+        _lib.check(self._L.sdcgym_vecnorm_accumulate(P, N, ld, planes_ptr, rms.mean.data_ptr(), self._scratch.data_ptr(),
+                                                     sums.data_ptr(), self._stream()), "vecnorm_accumulate")
+
+    def _merge(self, rms, P, total, sums):
+        _lib.check(self._L.sdcgym_vecnorm_merge(P, total, sums.data_ptr(), rms.mean.data_ptr(), rms.var.data_ptr(),
+                                                rms.count2.data_ptr(), self._stream()), "vecnorm_merge")
 
     def _normalize_planes(self, src, dst):
         v = self.venv
@@ -177,10 +186,21 @@ class VecNormalize:
         v, L, s = self.venv, self._L, self._stream()
         raw = v.step_tensor(actions)
         N = v.num_envs
+        # several ranks, both statistics live: accumulate both, ONE all-reduce (the only collective of a normalised
+        # step), merge both - instead of one collective per statistic
+        combined = self.training and self.norm_obs and self._multi_rank()
+        if combined:
+            self._accumulate(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
+            _lib.check(L.sdcgym_vecnorm_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(), s), "returns")
+            self._accumulate(self.ret_rms, self.returns.data_ptr(), 1, N, max(N, 1), self._rsums)
+            _dist_mod.all_reduce_sum(self._allsums)
+            total = self._global_count(N)
+            self._merge(self.obs_rms, self.P, total, self._sums)
+            self._merge(self.ret_rms, 1, total, self._rsums)
         if self.norm_obs:
             out = _StepOut(raw, self._normalized_terminal)
             del out["terminal"]
-            if self.training:
+            if self.training and not combined:
                 self._update(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
             dst = self.norm_planes
             if obs_out is not None:
@@ -195,7 +215,9 @@ class VecNormalize:
             out = dict(raw)
             out["obs_planes"] = v.S[:, :N]
         out["raw_reward"] = raw["reward"]
-        if self.training and self.fused_update and not self._multi_rank():
+        if combined:
+            pass  # return statistics already updated above
+        elif self.training and self.fused_update and not self._multi_rank():
             r = self.ret_rms
             _lib.check(L.sdcgym_vecnorm_update_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(),
                                                        r.mean.data_ptr(), r.var.data_ptr(), r.count2.data_ptr(),
