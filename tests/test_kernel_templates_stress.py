@@ -185,3 +185,53 @@ def test_pinv_in_side_store_formulation():
     _run("sdc-v0", 9, 150, prec_type="lower_tri", seed=31, entry="shim_step_hold9")
     _run("sdc-v0", 8, 150, prec="LU", seed=32, entry="shim_step_hold9")
     _run("sdc-v1", 9, 80, prec_type="strictly_lower_tri", steps=10, seed=33, entry="shim_step_hold9")
+
+
+@pytest.mark.parametrize("M", [3, 5, 7, 9])
+def test_spectral_radius_template_against_lapack_incl_singular_iteration_matrices(M):
+    """host build of rho_one (csrc/specrad.cuh): Householder-Hessenberg + shifted QR with real-cosine rotations and
+    the unshifted first step for numerically singular matrices (MIN, near-MIN, LU make Q - Qd (nearly) singular),
+    against numpy's zgeev: 1e-10 relative (dp_playground.py:216-228, sdc_env.py:421-425)."""
+    import ctypes
+    from sdc_gym_b200 import _lib
+    from sdc_gym_b200.precond import fixed_preconditioner, qdmat_from_output
+    L = host_shim.shim()
+    rng = np.random.default_rng(100 + M)
+    Q = collocation_matrix(M)
+
+    def check(prec_type, qd, Qds, lam, fixed=None):
+        n = lam.shape[0]
+        d = _lib.RhoDesc()
+        d.M, d.prec_type, d.dt = M, _lib.PREC_TYPES[prec_type], 1.0
+        d.qd_is_complex = int(qd is not None and np.iscomplexobj(qd))
+        for k, v in enumerate(Q.reshape(-1)):
+            d.Q[k] = v
+        if fixed is not None:
+            for k, v in enumerate(np.asarray(fixed, dtype=np.float64).reshape(-1)):
+                d.Qd_fixed[k] = v
+        rho = np.zeros(n)
+        qd_ptr = None if qd is None else np.ascontiguousarray(qd).ctypes.data
+        keep = None if qd is None else np.ascontiguousarray(qd)
+        assert L.shim_spectral_radius(ctypes.byref(d), n, lam.ctypes.data, None if keep is None else keep.ctypes.data,
+                                      rho.ctypes.data) == 0
+        for i in range(n):
+            K = lam[i] * np.linalg.inv(np.eye(M) - lam[i] * Qds[i]) @ (Q - Qds[i])
+            ref = max(abs(np.linalg.eigvals(K)))
+            assert abs(rho[i] - ref) <= 1e-10 * ref + 1e-14, (M, prec_type, i, rho[i], ref)
+
+    n = 60
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+    lam[0] = 0.0
+    # fixed preconditioners: MIN (M = 3, 5, 7) and LU give numerically singular Q - Qd
+    for prec in ("min", "LU", "EE", "zeros"):
+        Qd = fixed_preconditioner(prec, M, Q)
+        check("fixed", None, [Qd] * n, lam, fixed=Qd)
+    # learned diagonals next to MIN (nearly singular) and generic ones, real and complex
+    base = np.diag(fixed_preconditioner("min", M))
+    near = base[None] + rng.uniform(-1e-4, 1e-4, (n, M))
+    check("diag", near, [np.diag(x) for x in near], lam)
+    gen = rng.uniform(0.02, 0.5, (n, M)) + 1j * rng.uniform(-0.05, 0.05, (n, M))
+    check("diag", gen, [np.diag(x) for x in gen], lam)
+    A = num_actions(M, "lower_tri")
+    tri = rng.uniform(0.0, 0.3, (n, A))
+    check("lower_tri", tri, [qdmat_from_output(x, M, "lower_tri") for x in tri], lam)
