@@ -1,5 +1,8 @@
 // Experiment (host): how many QR steps, at which active size, does max_abs_eig<5> take on the lambda box?
-// g++ -O2 -std=c++17 -I sdc_gym_b200/csrc tools/qr_iteration_count.cpp -o /tmp/qrc && /tmp/qrc
+//   g++ -O2 -std=c++17 -I sdc_gym_b200/csrc tools/qr_iteration_count.cpp -o /tmp/qrc
+//   python -c "import numpy as np; from sdc_gym_b200.collocation import collocation_matrix as C; \
+//              from sdc_gym_b200.precond import fixed_preconditioner as F; \
+//              print(*map(float, C(5).ravel()), *map(float, np.diag(F('min', 5))))" | /tmp/qrc
 #include <cstdio>
 #include <cstdint>
 static long g_steps[8];
