@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 3 /* 3: SDCGYM_ACTION_* bits in do_scale, sdcgym_vecnorm_update[_returns], scratch + 2 */
+#define SDCGYM_ABI_VERSION 4 /* 4: result blocks (sdcgym_block_*, sdcgym_pipe_step_block), sdcgym_export_rows */
 #define SDCGYM_MAX_M 9
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -150,6 +150,10 @@ int sdcgym_step(const sdcgym_env_desc* desc, const sdcgym_state* st, const sdcgy
 /* planes S[4M][ld] -> reference observation layout obs[N][2][M] complex128 (interleaved re, im) and back */
 int sdcgym_export_obs(int M, int64_t N, int64_t ld, const double* S, double* obs, void* stream);
 int sdcgym_import_obs(int M, int64_t N, int64_t ld, const double* obs, double* S, void* stream);
+
+/* `P` consecutive planes X[P][ld] -> rows out[N][P] (env-major).  With X = S + 2M*ld and P = 2M this is the residual
+ * half of the observation, obs[:, 1, :] as [N][M] complex128; with X = S the u half, obs[:, 0, :]. */
+int sdcgym_export_rows(int P, int64_t N, int64_t ld, const double* X, double* out, void* stream);
 
 /* recompute resnorm = ||r||_inf from S (after a state injection) */
 int sdcgym_refresh_resnorm(int M, int64_t N, int64_t ld, const double* S, double* resnorm, void* stream);
@@ -289,6 +293,41 @@ typedef struct sdcgym_vecnorm {
 int sdcgym_pipe_step_vecnorm(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgym_state* st,
                              const sdcgym_step_io* dev, double* obs_dev, const sdcgym_host_io* host,
                              const sdcgym_vecnorm* vn, void* caller_stream);
+/*
+ * Result blocks: ONE contiguous buffer per side (device block, page-locked host block, same layout) holding everything a
+ * `DummyVecEnv.step` returns for N envs, so that a whole step's results leave the GPU in a single transfer (or, for large
+ * batches, in a few large chunked ones) and land where the host-side arrays already live - no pack kernel, no scatter:
+ *     obs_u    [N][M] complex128   observation row 0 (u)          obs[i, 0, :]
+ *     reward   [N] f64,  residual [N] f64,  lam [N][2] f64,  niter [N] i32,  flags [N] u8
+ *     obs_r    [N][M] complex128   observation row 1 (residual)   obs[i, 1, :]
+ * The reference observation (N, 2, M) complex128 is the strided view (strides 16M, obs_r - obs_u, 16 bytes) based at
+ * obs_u.  `skip_u`: for sdc-v0 with auto-reset the returned u row is identically 1 (sdc_env.py:306-314: every step ends
+ * the episode and the observation is the reset state), so the caller fills the host u rows ONCE and the step neither
+ * exports nor transfers them (117 instead of 197 bytes per env at M = 5).  All offsets are multiples of 256 bytes.
+ */
+typedef struct sdcgym_block_layout {
+    int64_t N;
+    int32_t M, reserved;
+    uint64_t obs_u, reward, residual, lam, niter, flags, obs_r, total; /* byte offsets; total = block size */
+} sdcgym_block_layout;
+int sdcgym_block_layout_init(int M, int64_t N, sdcgym_block_layout* out);
+
+typedef struct sdcgym_block_io {
+    unsigned char* dev_block;  /* device memory, layout.total bytes; the step writes its results here */
+    unsigned char* host_block; /* page-locked host memory, layout.total bytes */
+    double* action_dev;        /* device staging [N][A] ([N][A][2] complex) */
+    const double* action_host; /* host actions, same shape (page-locked for asynchronous upload) */
+    double* terminal_obs;      /* device planes [4M][ld] or NULL (terminal observations not kept) */
+    int32_t skip_u;            /* 1: u rows are constant, neither exported nor transferred */
+    int32_t chunks;            /* <= 0: chosen by the library from the batch size */
+} sdcgym_block_io;
+/* env.step with host actions in, host results out (see sdcgym_pipe_step); returns when the host block is filled.
+ * `vn` may be NULL.  With `vn` (see sdcgym_pipe_step_vecnorm) the host block receives the NORMALISED observation rows
+ * and reward; the device block keeps the raw reward, the observation rows of the device block are the normalised ones. */
+int sdcgym_pipe_step_block(sdcgym_pipe* pipe, const sdcgym_env_desc* desc, const sdcgym_state* st,
+                           const sdcgym_block_layout* layout, const sdcgym_block_io* bio, const sdcgym_vecnorm* vn,
+                           void* caller_stream);
+
 int sdcgym_host_alloc(size_t bytes, void** out); /* page-locked host memory */
 int sdcgym_host_free(void* p);
 

@@ -11,9 +11,12 @@ imports that file makes and that are not installed in this image:
   with ``.Qmat``, ``.delta_m``, ``.num_nodes`` (``sdc_env.py:11-12,53-54,186``), served by
   ``sdc_gym_b200.collocation`` so that reference and product share identical collocation bits.
 
-The reference directory exists only in the build container, never on the GPU box: everything that runs
-there uses the committed fixtures in ``tests/golden`` (made by ``tests/golden/make_golden.py`` through this
-loader) or the travelling restatements ``oracle/sdc_port.py`` / ``oracle/sdc_exact.c``.
+The reference directory exists only in the build container, never on the GPU box.  Parity there rests on the
+committed fixtures in ``tests/golden`` (made by ``tests/golden/make_golden.py`` through this loader) and the
+travelling restatements ``oracle/sdc_port.py`` / ``oracle/sdc_exact.c``.  For TIMING the reference on the GPU box's
+host cores (``bench.py --impl reference`` / ``cpu_baseline``), ``make -C oracle ref`` (run by
+``__graft_entry__.build()`` in the build container) stages the unmodified ``sdc_env.py`` into the git-ignored
+``oracle/_ref/``, which travels with the snapshot; ``reference_path()`` prefers the live tree and falls back to it.
 """
 from __future__ import annotations
 
@@ -28,8 +31,22 @@ REFERENCE_ROOT = os.environ.get("SDC_REFERENCE_ROOT", "/root/reference")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+STAGED_REF = os.path.join(_REPO, "oracle", "_ref", "sdc_env.py")
+
+
 def reference_available() -> bool:
+    """the live reference tree (build container only) - what parity tests and golden generation need"""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "sdc_gym", "envs", "sdc_env.py"))
+
+
+def reference_path(allow_staged: bool = True):
+    """path of the unmodified reference env module: the live tree, else the copy staged by ``make -C oracle ref``"""
+    live = os.path.join(REFERENCE_ROOT, "sdc_gym", "envs", "sdc_env.py")
+    if os.path.isfile(live):
+        return live
+    if allow_staged and os.path.isfile(STAGED_REF):
+        return STAGED_REF
+    return None
 
 
 def _install_stubs():
@@ -88,10 +105,10 @@ def load_reference_envs():
     global _cached
     if _cached is not None:
         return _cached
-    if not reference_available():
-        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT}")
+    path = reference_path()
+    if path is None:
+        raise FileNotFoundError(f"reference not found under {REFERENCE_ROOT} nor staged at {STAGED_REF}")
     _install_stubs()
-    path = os.path.join(REFERENCE_ROOT, "sdc_gym", "envs", "sdc_env.py")
     spec = importlib.util.spec_from_file_location("_reference_sdc_env", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

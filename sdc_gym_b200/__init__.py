@@ -21,7 +21,7 @@ REGISTRY = {
 }
 
 __all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts",
-           "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY"]
+           "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY", "register_gym"]
 
 
 def __getattr__(name):
@@ -47,6 +47,36 @@ def make(envname, num_envs=1, **kwargs):
         raise KeyError(f"unknown env id {envname!r}; registered: {sorted(REGISTRY)}")
     from .vec_env import SDCVecEnv
     return SDCVecEnv(envname, num_envs=num_envs, **kwargs)
+
+
+def register_gym(force=False):
+    """Optional shim for the reference's scripts: when ``gym`` (or ``gymnasium``) is importable, register the ids of
+    ``sdc_gym/__init__.py:3-13`` so that ``gym.make('sdc-v0', **kwargs)`` resolves to this package instead of the
+    numpy env.  The entry point builds a single-env ``SDCVecEnv`` (``num_envs=1``) behind a thin ``gym.Env`` adapter;
+    batched use goes through ``make`` / ``make_env``, which need no gym at all.  Returns the ids registered (an empty
+    list when no gym package is installed - never an error: gym is not a dependency of the path)."""
+    done = []
+    for modname in ("gym", "gymnasium"):
+        try:
+            gym = __import__(modname)
+            from importlib import import_module
+            registration = import_module(modname + ".envs.registration")
+        except Exception:
+            continue
+        registry = getattr(registration, "registry", {})
+        specs = getattr(registry, "env_specs", registry)
+        for env_id, (_cls, max_steps) in REGISTRY.items():
+            if env_id in specs and not force:
+                continue
+            if env_id in specs:
+                try:
+                    del specs[env_id]
+                except Exception:
+                    pass
+            gym.register(id=env_id, entry_point="sdc_gym_b200.gym_adapter:make_single",
+                         kwargs={"envname": env_id}, max_episode_steps=max_steps)
+            done.append(f"{modname}:{env_id}")
+    return done
 
 
 _ENV_ARGS = ("M", "dt", "restol", "lambda_real_interval", "lambda_imag_interval",

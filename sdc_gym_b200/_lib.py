@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
 
 MAX_M = 9
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -130,6 +130,69 @@ class HostIO(ctypes.Structure):
     ]
 
 
+class BlockLayout(ctypes.Structure):
+    """struct sdcgym_block_layout"""
+
+    _fields_ = [("N", ctypes.c_int64), ("M", ctypes.c_int32), ("reserved", ctypes.c_int32)] + [
+        (k, ctypes.c_uint64) for k in ("obs_u", "reward", "residual", "lam", "niter", "flags", "obs_r", "total")]
+
+
+class BlockIO(ctypes.Structure):
+    """struct sdcgym_block_io"""
+
+    _fields_ = [
+        ("dev_block", ctypes.c_void_p),
+        ("host_block", ctypes.c_void_p),
+        ("action_dev", ctypes.c_void_p),
+        ("action_host", ctypes.c_void_p),
+        ("terminal_obs", ctypes.c_void_p),
+        ("skip_u", ctypes.c_int32),
+        ("chunks", ctypes.c_int32),
+    ]
+
+
+class DeviceGuard:
+    """Makes ``device`` the current CUDA device for the duration of a ``with`` block (re-entrant, no-op when it
+    already is): the C ABI launches on the calling thread's current device, streams and buffers belong to the
+    env's device."""
+
+    __slots__ = ("idx", "_stack", "_cuda")
+
+    def __init__(self, device):
+        import torch
+
+        self._cuda = torch.cuda
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self._stack = []
+
+    def __enter__(self):
+        cur = self._cuda.current_device()
+        if cur != self.idx:
+            self._cuda.set_device(self.idx)
+            self._stack.append(cur)
+        else:
+            self._stack.append(-1)
+        return self
+
+    def __exit__(self, *exc):
+        prev = self._stack.pop()
+        if prev >= 0:
+            self._cuda.set_device(prev)
+        return False
+
+
+def on_device(fn):
+    """Method decorator: run with ``self._guard`` (a DeviceGuard) held."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with self._guard:
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class VecNorm(ctypes.Structure):
     """struct sdcgym_vecnorm"""
 
@@ -201,6 +264,12 @@ def load():
                                    ctypes.POINTER(HostIO), ctypes.c_int, vp]
     L.sdcgym_pipe_step_vecnorm.argtypes = [vp, ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(StepIO), vp,
                                            ctypes.POINTER(HostIO), ctypes.POINTER(VecNorm), vp]
+    L.sdcgym_export_rows.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp]
+    L.sdcgym_block_layout_init.argtypes = [ctypes.c_int, i64, ctypes.POINTER(BlockLayout)]
+    L.sdcgym_pipe_step_block.argtypes = [vp, ctypes.POINTER(EnvDesc), ctypes.POINTER(State), ctypes.POINTER(BlockLayout),
+                                         ctypes.POINTER(BlockIO), ctypes.POINTER(VecNorm), vp]
+    for name in ("sdcgym_export_rows", "sdcgym_block_layout_init", "sdcgym_pipe_step_block"):
+        getattr(L, name).restype = ctypes.c_int
     L.sdcgym_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.sdcgym_host_free.argtypes = [vp]
     for name in ("sdcgym_pipe_create", "sdcgym_pipe_destroy", "sdcgym_pipe_step", "sdcgym_pipe_step_vecnorm",

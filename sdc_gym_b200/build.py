@@ -25,8 +25,6 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 NVCC_FLAGS += os.environ.get("SDCGYM_EXTRA_NVCC_FLAGS", "").split()  # experiments only
-if os.environ.get("SDCGYM_TUNE_VARIANTS") == "1":  # experiment builds only: extra (occupancy, residency) variants
-    NVCC_FLAGS.append("-DSDCGYM_TUNE_VARIANTS")
 
 
 def _nvcc() -> str:

@@ -182,6 +182,14 @@ static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdc
     if (!p || !desc || !st || !dev || !host) return SDCGYM_ENULL;
     const int64_t N = st->N;
     if (N < 0 || chunks < 1) return SDCGYM_EINVAL;
+    int cur_dev = -1;
+    PIPE_CHECK(cudaGetDevice(&cur_dev));
+    if (cur_dev != p->device) {  // streams, events and staging live on the device the pipe was created on
+        PIPE_CHECK(cudaSetDevice(p->device));
+        const int rc = pipe_step_impl(p, desc, st, dev, obs_dev, host, chunks, vn, caller_stream);
+        cudaSetDevice(cur_dev);
+        return rc;
+    }
     if (chunks > p->max_chunks) chunks = p->max_chunks;
     if (N == 0) return 0;
     const int M = desc->M;
@@ -330,6 +338,197 @@ static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdc
     PIPE_CHECK(cudaStreamSynchronize(p->s_out));
     PIPE_CHECK(cudaStreamSynchronize(p->s_out2));
     // later work on the caller's stream must see the new state
+    PIPE_CHECK(cudaEventRecord(p->ev_start, p->s_k));
+    PIPE_CHECK(cudaStreamWaitEvent(cs, p->ev_start, 0));
+    return 0;
+}
+
+
+// =====================================================================================================================
+// Result blocks (include/sdcgym.h: sdcgym_block_*): the device-side results of a step and the host arrays the caller
+// reads are two copies of ONE contiguous layout, so a step's results leave in a single transfer (small / mid-size
+// batches) or in a few large chunked ones (large batches), and land where the host-side arrays already live.
+// =====================================================================================================================
+static inline uint64_t align256(uint64_t x) { return (x + 255u) / 256u * 256u; }
+
+extern "C" int sdcgym_block_layout_init(int M, int64_t N, sdcgym_block_layout* L) {
+    if (!L) return SDCGYM_ENULL;
+    if (M < 1 || M > SDCGYM_MAX_M || N < 0) return SDCGYM_EINVAL;
+    const uint64_t n = (uint64_t)N;
+    uint64_t o = 0;
+    L->N = N;
+    L->M = M;
+    L->reserved = 0;
+    L->obs_u = o;    o += align256(n * 2 * M * sizeof(double));
+    L->reward = o;   o += align256(n * sizeof(double));
+    L->residual = o; o += align256(n * sizeof(double));
+    L->lam = o;      o += align256(n * 2 * sizeof(double));
+    L->niter = o;    o += align256(n * sizeof(int32_t));
+    L->flags = o;    o += align256(n);
+    L->obs_r = o;    o += align256(n * 2 * M * sizeof(double));
+    L->total = o;
+    return 0;
+}
+
+namespace {
+// the pipe's streams, events and staging belong to the device it was created on: make that device current for the call
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int want) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != want) {
+            err = cudaSetDevice(want);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int auto_chunks(int64_t N) {
+    // one transfer up to 32 k envs (<= ~4 MB of results: the copy is shorter than the extra launches and events of a
+    // pipeline); beyond that overlap H2D | kernels | D2H in 2..8 growing chunks (profiles/e2e_sweep_r02.jsonl)
+    if (N < 32768) return 1;
+    if (N < 98304) return 2;
+    if (N < 393216) return 4;
+    return 8;
+}
+}  // namespace
+
+extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdcgym_state* st,
+                                      const sdcgym_block_layout* L, const sdcgym_block_io* bio, const sdcgym_vecnorm* vn,
+                                      void* caller_stream) {
+    if (!p || !desc || !st || !L || !bio) return SDCGYM_ENULL;
+    const int64_t N = st->N;
+    const int M = desc->M;
+    if (N < 0 || L->N != N || L->M != M) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!bio->dev_block || !bio->host_block) return SDCGYM_ENULL;
+    const int A = sdcgym_num_actions(M, desc->prec_type);
+    const int aw = A * (desc->action_is_complex ? 2 : 1);  // doubles per env in the action arrays
+    if (A > 0 && (!bio->action_host || !bio->action_dev)) return SDCGYM_ENULL;
+    if (vn) {
+        if (!vn->out_reward || !vn->returns || !vn->ret_var) return SDCGYM_ENULL;
+        if (vn->norm_obs && (!vn->out_planes || !vn->obs_mean || !vn->obs_var)) return SDCGYM_ENULL;
+        if (vn->training && (!vn->ret_mean || !vn->ret_count2 || !vn->scratch_ret || !vn->sums_ret)) return SDCGYM_ENULL;
+        if (vn->training && vn->norm_obs && (!vn->obs_count2 || !vn->scratch_obs || !vn->sums_obs)) return SDCGYM_ENULL;
+    }
+    DeviceScope scope(p->device);
+    if (scope.err != cudaSuccess) return (int)scope.err;
+    cudaStream_t cs = (cudaStream_t)caller_stream;
+    unsigned char* db = bio->dev_block;
+    unsigned char* hb = bio->host_block;
+    const bool skip_u = bio->skip_u != 0 && !(vn && vn->norm_obs);  // normalised u rows are not constant
+    const int P2 = 2 * M;                                            // planes per observation row (u or r)
+    const size_t row_bytes = (size_t)P2 * sizeof(double);
+
+    sdcgym_step_io io;
+    io.action = A > 0 ? bio->action_dev : nullptr;
+    io.action_env_stride = aw;
+    io.action_comp_stride = desc->action_is_complex ? 2 : 1;
+    io.reward = reinterpret_cast<double*>(db + L->reward);
+    io.flags = db + L->flags;
+    io.info_residual = reinterpret_cast<double*>(db + L->residual);
+    io.info_niter = reinterpret_cast<int32_t*>(db + L->niter);
+    io.info_lam = reinterpret_cast<double*>(db + L->lam);
+    io.terminal_obs = bio->terminal_obs;
+    io.old_states = nullptr;
+    double* obs_u_dev = reinterpret_cast<double*>(db + L->obs_u);
+    double* obs_r_dev = reinterpret_cast<double*>(db + L->obs_r);
+
+    int chunks = bio->chunks > 0 ? bio->chunks : auto_chunks(N);
+    if (chunks > p->max_chunks) chunks = p->max_chunks;
+    if (vn) chunks = 1;  // the statistics need the whole batch before any observation can leave
+
+    if (chunks == 1) {
+        // ---- upload, step, export, ONE download; everything in order on the caller's stream ----
+        if (A > 0)
+            PIPE_CHECK(cudaMemcpyAsync(bio->action_dev, bio->action_host, sizeof(double) * N * aw, cudaMemcpyHostToDevice, cs));
+        int rc = sdcgym_step(desc, st, &io, cs);
+        if (rc) return rc;
+        const double* planes = st->S;
+        if (vn) {
+            rc = run_vecnorm(desc, st, &io, vn, cs);
+            if (rc) return rc;
+            if (vn->norm_obs) planes = vn->out_planes;
+        }
+        if (!skip_u) {
+            rc = sdcgym_export_rows(P2, N, st->ld, planes, obs_u_dev, cs);
+            if (rc) return rc;
+        }
+        rc = sdcgym_export_rows(P2, N, st->ld, planes + (size_t)P2 * st->ld, obs_r_dev, cs);
+        if (rc) return rc;
+        const uint64_t first = skip_u ? L->reward : 0;
+        PIPE_CHECK(cudaMemcpyAsync(hb + first, db + first, L->total - first, cudaMemcpyDeviceToHost, cs));
+        if (vn)  // the host sees the normalised reward; the device block keeps the raw one
+            PIPE_CHECK(cudaMemcpyAsync(hb + L->reward, vn->out_reward, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, cs));
+        PIPE_CHECK(cudaStreamSynchronize(cs));
+        return 0;
+    }
+
+    // ---- large batch: H2D(actions) | step + export kernels | D2H(results), chunk by chunk over four streams ----
+    PIPE_CHECK(cudaEventRecord(p->ev_start, cs));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_start, 0));
+    PIPE_CHECK(cudaStreamWaitEvent(p->s_out2, p->ev_start, 0));
+    const int group = chunks >= 4 ? chunks / 2 : chunks;  // the five small arrays leave once per group of chunks
+    int64_t small_lo = 0;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t lo = chunk_begin(N, c, chunks), hi = chunk_begin(N, c + 1, chunks);
+        if (hi <= lo) continue;
+        const int64_t n = hi - lo;
+        if (A > 0) {
+            PIPE_CHECK(cudaMemcpyAsync(bio->action_dev + lo * aw, bio->action_host + lo * aw, sizeof(double) * n * aw,
+                                       cudaMemcpyHostToDevice, p->s_in));
+            PIPE_CHECK(cudaEventRecord(p->ev_in[c], p->s_in));
+            PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[c], 0));
+        }
+        sdcgym_state s2 = *st;
+        s2.N = n;
+        s2.lam += lo; s2.S += lo; s2.resnorm += lo; s2.niter += lo; s2.episodes += lo; s2.rng_ctr += lo;
+        sdcgym_step_io io2 = io;
+        if (A > 0) io2.action = bio->action_dev + lo * aw;
+        io2.reward += lo;
+        io2.flags += lo;
+        io2.info_residual += lo;
+        io2.info_niter += lo;
+        io2.info_lam += 2 * lo;
+        if (io2.terminal_obs) io2.terminal_obs += lo;
+        sdcgym_env_desc d2 = *desc;
+        d2.env_offset += lo;
+        int rc = sdcgym_step(&d2, &s2, &io2, p->s_k);
+        if (rc) return rc;
+        if (!skip_u) {
+            rc = sdcgym_export_rows(P2, n, st->ld, st->S + lo, obs_u_dev + lo * P2, p->s_k);
+            if (rc) return rc;
+        }
+        rc = sdcgym_export_rows(P2, n, st->ld, st->S + (size_t)P2 * st->ld + lo, obs_r_dev + lo * P2, p->s_k);
+        if (rc) return rc;
+        PIPE_CHECK(cudaEventRecord(p->ev_k[c], p->s_k));
+        PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[c], 0));
+#define SEG(strm, off, from, count, bytes_per_env)                                                         \
+    PIPE_CHECK(cudaMemcpyAsync(hb + (off) + (size_t)(from) * (bytes_per_env), db + (off) + (size_t)(from) * (bytes_per_env), \
+                               (size_t)(count) * (bytes_per_env), cudaMemcpyDeviceToHost, strm));
+        SEG(p->s_out, L->obs_r, lo, n, row_bytes)
+        if (!skip_u) SEG(p->s_out, L->obs_u, lo, n, row_bytes)
+        if ((c + 1) % group == 0 || c + 1 == chunks) {
+            PIPE_CHECK(cudaStreamWaitEvent(p->s_out2, p->ev_k[c], 0));
+            const int64_t sn = hi - small_lo;
+            SEG(p->s_out2, L->reward, small_lo, sn, sizeof(double))
+            SEG(p->s_out2, L->flags, small_lo, sn, 1)
+            SEG(p->s_out2, L->niter, small_lo, sn, sizeof(int32_t))
+            SEG(p->s_out2, L->residual, small_lo, sn, sizeof(double))
+            SEG(p->s_out2, L->lam, small_lo, sn, 2 * sizeof(double))
+            small_lo = hi;
+        }
+#undef SEG
+    }
+    PIPE_CHECK(cudaStreamSynchronize(p->s_out));
+    PIPE_CHECK(cudaStreamSynchronize(p->s_out2));
     PIPE_CHECK(cudaEventRecord(p->ev_start, p->s_k));
     PIPE_CHECK(cudaStreamWaitEvent(cs, p->ev_start, 0));
     return 0;

@@ -195,6 +195,15 @@ extern "C" int sdcgym_export_obs(int M, int64_t N, int64_t ld, const double* S, 
     return (int)cudaGetLastError();
 }
 
+extern "C" int sdcgym_export_rows(int P, int64_t N, int64_t ld, const double* X, double* out, void* stream) {
+    if (P < 1 || P > 4 * SDCGYM_MAX_M || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if (N == 0) return 0;
+    if (!X || !out) return SDCGYM_ENULL;
+    const unsigned grid = (unsigned)((N + kTileEnvs - 1) / kTileEnvs);
+    export_obs_kernel<<<grid, kTileEnvs, P * (kTileEnvs + 1) * sizeof(double), (cudaStream_t)stream>>>(P, N, ld, X, out);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int sdcgym_import_obs(int M, int64_t N, int64_t ld, const double* obs, double* S, void* stream) {
     if (M < 1 || M > SDCGYM_MAX_M || N < 0 || ld < N) return SDCGYM_EINVAL;
     if (N == 0) return 0;

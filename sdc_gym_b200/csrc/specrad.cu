@@ -44,9 +44,9 @@ extern "C" int sdcgym_spectral_radius(const sdcgym_rho_desc* d, int64_t N, const
     if (!d) return SDCGYM_ENULL;
     if (!sdcgym_supported(d->M, d->prec_type)) return SDCGYM_EUNSUPPORTED;
     if (N < 0) return SDCGYM_EINVAL;
+    if (N == 0) return 0;  // an empty shard (dist.shard_range allows them) is a no-op, whatever the other arguments
     if (!lam && (d->grid_re <= 0 || d->grid_im <= 0 || d->grid_first < 0 || d->grid_first + N > d->grid_re * d->grid_im))
         return SDCGYM_EINVAL;
-    if (N == 0) return 0;
     if (!rho) return SDCGYM_ENULL;
     if (d->prec_type != SDCGYM_PREC_FIXED && !qd) return SDCGYM_ENULL;
     if (d->prec_type == SDCGYM_PREC_FIXED) {

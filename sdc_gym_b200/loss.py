@@ -49,6 +49,7 @@ class SpectralRadiusLoss:
             for k, v in enumerate(fixed_preconditioner(prec, self.M, self.Q).reshape(-1)):
                 d.Qd_fixed[k] = float(v)
         self._desc = d
+        self._guard = _lib.DeviceGuard(self.device)
 
     def _stream(self):
         return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
@@ -71,12 +72,15 @@ class SpectralRadiusLoss:
         t = t.contiguous()
         return (torch.view_as_real(t).contiguous() if is_c else t), int(is_c), broadcast
 
+    @_lib.on_device
     def spectral_radii(self, lams, outputs=None):
         """rho per sample as a CUDA float64 tensor (B,).  ``lams``: (B,) or (B, 1) complex (numpy or torch)."""
         torch = _torch()
         lam = lams if isinstance(lams, torch.Tensor) else torch.as_tensor(np.asarray(lams, dtype=np.complex128))
         lam = lam.to(self.device).to(torch.complex128).reshape(-1).contiguous()
         B = lam.numel()
+        if B == 0:  # an empty shard: nothing to launch (a NULL lambda pointer would select grid mode in the ABI)
+            return torch.empty(0, dtype=torch.float64, device=self.device)
         qd, is_c, bc = self._outputs_tensor(outputs, B)
         d = self._desc
         d.qd_is_complex, d.qd_broadcast = is_c, bc
@@ -94,6 +98,7 @@ class SpectralRadiusLoss:
         rho = self.spectral_radii(lams, outputs)
         return self.mean(rho)
 
+    @_lib.on_device
     def radii_and_grads(self, lams, outputs):
         """(rho (B,), g (B, n_out) complex128) with d rho_b = Re(sum_k g_bk d output_bk): per-sample spectral
         radius and its derivative with respect to the Q_delta parameters (left/right eigenvector formula,
@@ -104,6 +109,9 @@ class SpectralRadiusLoss:
         lam = lams if isinstance(lams, torch.Tensor) else torch.as_tensor(np.asarray(lams, dtype=np.complex128))
         lam = lam.detach().to(self.device).to(torch.complex128).reshape(-1).contiguous()
         B = lam.numel()
+        if B == 0:
+            return (torch.empty(0, dtype=torch.float64, device=self.device),
+                    torch.empty((0, self.n_out), dtype=torch.complex128, device=self.device))
         out = outputs.detach() if isinstance(outputs, torch.Tensor) else outputs
         qd, is_c, bc = self._outputs_tensor(out, B)
         if bc:
@@ -141,6 +149,7 @@ class SpectralRadiusLoss:
         ``requires_grad``) - forward and backward both run the hand-written kernels."""
         return _SpectralRadiusFn.apply(outputs, self, lams)
 
+    @_lib.on_device
     def _sum(self, rho):
         """deterministic fp64 sum (fixed reduction tree) as a CUDA scalar"""
         torch = _torch()
@@ -154,6 +163,7 @@ class SpectralRadiusLoss:
     def mean(self, rho):
         return self._sum(rho) / rho.numel()
 
+    @_lib.on_device
     def grid(self, n_re, n_im, lambda_real_interval, lambda_imag_interval, output=None, rows=None):
         """rho on the (n_re x n_im) tensor grid over the lambda box for ONE Q_delta parameter row (or the fixed
         ``prec``): lambdas are generated from the grid index on the device (0 bytes in, 8 bytes out per matrix).
@@ -234,6 +244,7 @@ class ResidualLoss:
         self._sr = SpectralRadiusLoss(M, dt, prec_type, prec=prec, Q=Q, device=device)
         self.M, self.dt, self.prec_type = self._sr.M, self._sr.dt, self._sr.prec_type
         self.Q, self.device = self._sr.Q, self._sr.device
+        self._guard = self._sr._guard
 
     def _c128(self, x, shape):
         torch = _torch()
@@ -241,6 +252,7 @@ class ResidualLoss:
         t = t.to(self.device).to(torch.complex128).reshape(shape).contiguous()
         return torch.view_as_real(t)
 
+    @_lib.on_device
     def take_step(self, lams, outputs, Cs, u0s, us, old_residuals, with_grad=False):
         torch = _torch()
         sr, M = self._sr, self.M

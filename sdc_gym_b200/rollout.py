@@ -44,6 +44,7 @@ class RolloutBuffer:
         self.pos = 0
         self.full = False
         self._L = _lib.load()
+        self._guard = _lib.DeviceGuard(self.device)
 
     def reset(self):
         self.pos, self.full = 0, False
@@ -65,6 +66,7 @@ class RolloutBuffer:
         self.pos += 1
         self.full = self.pos == self.n_steps
 
+    @_lib.on_device
     def compute_returns_and_advantage(self, last_values, dones):
         """SB3 ``RolloutBuffer.compute_returns_and_advantage(last_values, dones)`` on the device."""
         torch = _torch()

@@ -16,6 +16,8 @@ reference's (``sdc_env.py:27-46``) plus ``prec_type`` (``dp_playground.py:194-20
 from __future__ import annotations
 
 import ctypes
+import os
+import sys
 from typing import Optional, Sequence
 
 import numpy as np
@@ -85,6 +87,45 @@ class LazyInfos(Sequence):
                 d["TimeLimit.truncated"] = False
             d["terminal_observation"] = self.terminal_observations()[i]
         return d
+
+
+class _HostSet:
+    """One page-locked host result block (layout ``sdcgym_block_layout``, include/sdcgym.h) and the numpy arrays a
+    ``step`` hands out as views of it.  The observation is the strided view (N, 2, M) complex128 over the u rows and
+    the residual rows of the block.
+
+    ``free()`` tells whether the caller still holds any of the arrays handed out (or a view derived from them): every
+    such view keeps a reference to ``root`` or to the array itself, so the reference counts are back at their
+    construction-time values exactly when nothing outside this object can observe the memory any more."""
+
+    def __init__(self, torch, layout, N, M, const_u):
+        self.blk = torch.zeros(int(layout.total), dtype=torch.uint8, pin_memory=True)
+        self.ptr = self.blk.data_ptr()
+        root = self.blk.numpy()
+        self.root = root
+
+        def seg(off, nbytes, dtype):
+            return root[int(off): int(off) + nbytes].view(dtype)
+
+        u_rows = seg(layout.obs_u, N * M * 16, np.complex128)
+        if const_u:
+            u_rows[:] = 1.0  # sdc-v0 + auto-reset: the returned u is the reset state, filled once, never transferred
+        self.obs = np.lib.stride_tricks.as_strided(u_rows, shape=(N, 2, M),
+                                                   strides=(16 * M, int(layout.obs_r - layout.obs_u), 16))
+        self.reward = seg(layout.reward, N * 8, np.float64)
+        self.residual = seg(layout.residual, N * 8, np.float64)
+        self.lam = seg(layout.lam, N * 16, np.complex128)
+        self.niter = seg(layout.niter, N * 4, np.int32)
+        self.flags = seg(layout.flags, N, np.uint8)
+        del u_rows, root
+        self._handed = (self.obs, self.reward, self.residual, self.lam, self.niter, self.flags)
+        self._baseline = self._counts()
+
+    def _counts(self):
+        return [sys.getrefcount(self.root)] + [sys.getrefcount(h) for h in self._handed]
+
+    def free(self):
+        return self._counts() == self._baseline
 
 
 class _TruncatedKey:
@@ -189,6 +230,8 @@ class SDCVecEnv:
         reuse_buffers: bool = False,
         pipeline_chunks: int = 0,
         host_pipeline: str = "native",
+        max_host_sets: int = 4,
+        keep_terminal: bool = True,
     ):
         torch = _torch()
         if envname not in _lib.ENV_KINDS:
@@ -252,12 +295,23 @@ class SDCVecEnv:
             self.niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
             self.episodes = torch.zeros(self.ld, dtype=torch.int32, device=dev)
             self.rng_ctr = torch.zeros(self.ld, dtype=torch.int32, device=dev)
-            self.reward = torch.zeros(self.ld, dtype=f64, device=dev)
-            self.flags = torch.zeros(self.ld, dtype=torch.uint8, device=dev)
-            self.info_residual = torch.zeros(self.ld, dtype=f64, device=dev)
-            self.info_niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
-            self.info_lam = torch.zeros((self.ld, 2), dtype=f64, device=dev)
-            self.terminal = torch.zeros((4 * self.M, self.ld), dtype=f64, device=dev)
+            # results of a step: ONE device block (include/sdcgym.h: sdcgym_block_layout) whose host twin is what
+            # `step` hands out, so a step's results leave the GPU in a single transfer; the per-array tensors below
+            # are views of it
+            self._layout = _lib.BlockLayout()
+            _lib.check(self._L.sdcgym_block_layout_init(self.M, N, ctypes.byref(self._layout)), "sdcgym_block_layout_init")
+            lay = self._layout
+            self.dev_block = torch.zeros(max(1, int(lay.total)), dtype=torch.uint8, device=dev)
+
+            def seg(off, nbytes, dtype):
+                return self.dev_block[int(off): int(off) + nbytes].view(dtype)
+
+            self.reward = seg(lay.reward, N * 8, f64)
+            self.flags = seg(lay.flags, N, torch.uint8)
+            self.info_residual = seg(lay.residual, N * 8, f64)
+            self.info_niter = seg(lay.niter, N * 4, torch.int32)
+            self.info_lam = seg(lay.lam, N * 16, f64).view(N, 2)
+            self.terminal = torch.zeros((4 * self.M, self.ld), dtype=f64, device=dev) if keep_terminal else None
             self.obs_aos = torch.zeros((N, 2, self.M, 2), dtype=f64, device=dev)
             a_w = max(1, self._kernel_n_act) * (2 if free_action_space else 1)
             self.action_dev = torch.zeros((N, a_w), dtype=f64, device=dev)
@@ -267,13 +321,17 @@ class SDCVecEnv:
         self._snap = None
         self._init_res = None
         self._pending = None
-        self._streams = None
         self.pipeline_chunks = int(pipeline_chunks)
-        if host_pipeline not in ("native", "torch"):
-            raise ValueError("host_pipeline must be 'native' (sdcgym_pipe_step) or 'torch' (torch streams)")
+        if host_pipeline != "native":
+            raise ValueError("host_pipeline: only 'native' (sdcgym_pipe_step_block inside libsdcgym.so) exists")
         self.host_pipeline = host_pipeline
+        self.max_host_sets = max(1, int(max_host_sets))
+        self.keep_terminal = bool(keep_terminal)
         self._pipe = None
-        self._pipe_args = None
+        self._bio = None
+        self._step_count = 0
+        self._term_aos = None
+        self.host_set_copies = 0  # steps that had to copy their outputs (all host sets still referenced by the caller)
 
         self._desc = _lib.EnvDesc()
         d = self._desc
@@ -298,7 +356,10 @@ class SDCVecEnv:
         d.lam_im_lo, d.lam_im_hi = float(lambda_imag_interval[0]), float(lambda_imag_interval[1])
         if lambda_real_interpolation_interval is not None:
             d.interp_x0, d.interp_x1 = (float(v) for v in lambda_real_interpolation_interval)
-        d.seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        # seed=None: fresh OS entropy like the reference's gym seeding (every env built without a seed differs);
+        # the key actually used is kept in `seed_used` so a run can be reproduced
+        self.seed_used = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        d.seed = self.seed_used
         d.env_offset = int(env_offset)
         for k, v in enumerate(self.Q.reshape(-1)):
             d.Q[k] = float(v)
@@ -306,6 +367,10 @@ class SDCVecEnv:
             d.Qd_fixed[k] = float(v)
         self.blas_variant = d.blas_variant
         self.envs = _EnvProxies(self)
+        # sdc-v0 with the fused auto-reset: every step ends the episode, the returned observation is the reset state
+        # of the next lambda, whose u row is identically 1 (sdc_env.py:306-314) - never exported, never transferred
+        self._const_u = bool(envname == "sdc-v0" and d.autoreset)
+        self._guard = _lib.DeviceGuard(self.device)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -336,13 +401,16 @@ class SDCVecEnv:
         self._init_res = None
 
     # ------------------------------------------------------------------ reset / seed
+    @_lib.on_device
     def seed(self, seed=None):
         """DummyVecEnv.seed: env i gets ``seed + i`` in the reference; here one Philox key for the batch."""
-        self._desc.seed = (0 if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self.seed_used = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._desc.seed = self.seed_used
         self.rng_ctr.zero_()
         # DummyVecEnv returns the per-env seeds; a lazy range instead of a list of num_envs integers
         return [None] * self.num_envs if seed is None else range(int(seed), int(seed) + self.num_envs)
 
+    @_lib.on_device
     def set_num_episodes(self, num_episodes, indices=None):
         if indices is None:
             self.episodes.fill_(int(num_episodes))
@@ -351,6 +419,7 @@ class SDCVecEnv:
             self.episodes[idx] = int(num_episodes)
         self._invalidate()
 
+    @_lib.on_device
     def reset(self, lam=None, mask=None):
         """Reset all envs (or those with ``mask``); ``lam`` (N,) complex injects the lambdas instead of drawing."""
         torch = _torch()
@@ -382,6 +451,7 @@ class SDCVecEnv:
                                              self.obs_aos.data_ptr() + 8 * start * 4 * self.M, self._stream()),
                    "sdcgym_export_obs")
 
+    @_lib.on_device
     def observation_tensor(self):
         """Current observation as a CUDA complex128 tensor (N, 2, M) (or (N, 2M, 50) with collect_states)."""
         torch = _torch()
@@ -396,6 +466,7 @@ class SDCVecEnv:
             return t
         return t.cpu().numpy()
 
+    @_lib.on_device
     def _snapshot(self):
         if self._snap is None:
             torch = _torch()
@@ -407,6 +478,7 @@ class SDCVecEnv:
                               episodes=self.episodes[:N].cpu().numpy())
         return self._snap
 
+    @_lib.on_device
     def _initial_residuals(self):
         if self._init_res is None:
             # r0 is a function of lambda only: run the reset kernel on scratch planes with lambda injected
@@ -436,7 +508,7 @@ class SDCVecEnv:
         io.info_residual = self.info_residual.data_ptr() + 8 * start
         io.info_niter = self.info_niter.data_ptr() + 4 * start
         io.info_lam = self.info_lam.data_ptr() + 16 * start
-        io.terminal_obs = (self.terminal.data_ptr() + 8 * start) if want_terminal else None
+        io.terminal_obs = (self.terminal.data_ptr() + 8 * start) if (want_terminal and self.terminal is not None) else None
         io.old_states = (self.old_states.data_ptr() + 8 * start * 2 * self.M * self.max_iters * 2
                          if self.old_states is not None else None)
         st = self._state(start, count)
@@ -444,6 +516,7 @@ class SDCVecEnv:
         _lib.check(self._L.sdcgym_step(ctypes.byref(d), ctypes.byref(st), ctypes.byref(io), self._stream()),
                    "sdcgym_step")
 
+    @_lib.on_device
     def step_tensor(self, actions=None, want_terminal=True):
         """Device-resident step: ``actions`` is a CUDA float64 (N, A) / complex128 (N, A) tensor (ignored for
         fixed ``prec``).  Nothing is copied to the host and nothing synchronises.  Returns a dict of CUDA
@@ -475,10 +548,13 @@ class SDCVecEnv:
             self._apply_spectral_radius_reward(actions if self._kernel_n_act else None)
         if self.collect_states and self.autoreset:
             self._reset_done_envs()
+        self._step_count += 1
         self._invalidate()
-        return dict(reward=self.reward[:N], flags=self.flags[:N], niter=self.info_niter[:N],
-                    residual=self.info_residual[:N], lam=torch.view_as_complex(self.info_lam)[:N],
-                    terminal=self.terminal[:, :N])
+        out = dict(reward=self.reward[:N], flags=self.flags[:N], niter=self.info_niter[:N],
+                   residual=self.info_residual[:N], lam=torch.view_as_complex(self.info_lam)[:N])
+        if self.terminal is not None:
+            out["terminal"] = self.terminal[:, :N]
+        return out
 
     def _apply_spectral_radius_reward(self, actions_t):
         """reward = rho(lam*dt*Pinv (Q - Qd)) for every env that did not err (reference reward_func :459-460)."""
@@ -512,30 +588,36 @@ class SDCVecEnv:
     def _ensure_host(self):
         if self._host is None:
             torch = _torch()
-            N, M = self.num_envs, self.M
-            pin = dict(pin_memory=True)
-            a_w = self.action_dev.shape[1]
-            self._host = dict(
-                action=torch.zeros((N, a_w), dtype=torch.float64, **pin),
-                actions=[],
-                obs=torch.zeros((N, 2, M, 2), dtype=torch.float64, **pin),
-                reward=torch.zeros(N, dtype=torch.float64, **pin),
-                flags=torch.zeros(N, dtype=torch.uint8, **pin),
-                niter=torch.zeros(N, dtype=torch.int32, **pin),
-                residual=torch.zeros(N, dtype=torch.float64, **pin),
-                lam=torch.zeros((N, 2), dtype=torch.float64, **pin),
-            )
-            self._host["actions"].append(self._host["action"])
-            # numpy views are built once: tensor.numpy() / .view() per step would cost more than a small batch's kernels
-            h = self._host
-            h["np"] = dict(
-                obs=h["obs"].numpy().view(np.complex128).reshape(N, 2, M), reward=h["reward"].numpy(),
-                flags=h["flags"].numpy(), niter=h["niter"].numpy(), residual=h["residual"].numpy(),
-                lam=h["lam"].numpy().view(np.complex128).reshape(N))
-            h["action_np"] = [h["action"].numpy()]
-            h["action_ptr"] = [h["action"].data_ptr()]
-            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            act = torch.zeros((self.num_envs, self.action_dev.shape[1]), dtype=torch.float64, pin_memory=True)
+            # numpy views / pointers are built once: tensor.numpy() per step would cost more than a small batch's kernels
+            self._host = dict(actions=[act], action_np=[act.numpy()], action_ptr=[act.data_ptr()], sets=[], spill=None)
         return self._host
+
+    def _new_set(self):
+        return _HostSet(_torch(), self._layout, self.num_envs, self.M, self._const_u)
+
+    def _acquire_set(self, host):
+        """(result set, owned): a page-locked result block that nothing outside the env references any more.
+
+        ``DummyVecEnv.step`` returns arrays the caller owns; copying 123 MB per step (2^20 envs) to honour that costs
+        five times the transfer itself.  Instead the step writes into a block whose arrays the caller has let go of
+        (reference counts, ``_HostSet.free``) - a loop that rebinds ``obs, rew, done, info = env.step(a)`` ping-pongs
+        between two blocks; a caller that keeps every result alive gets up to ``max_host_sets`` blocks and real copies
+        after that (``host_set_copies`` counts those steps).  ``reuse_buffers=True`` always uses block 0."""
+        sets = host["sets"]
+        if self.reuse_buffers:
+            if not sets:
+                sets.append(self._new_set())
+            return sets[0], True
+        for hs in sets:
+            if hs.free():
+                return hs, True
+        if len(sets) < self.max_host_sets:
+            sets.append(self._new_set())
+            return sets[-1], True
+        if host["spill"] is None:
+            host["spill"] = self._new_set()
+        return host["spill"], False
 
     def pinned_action_buffer(self, index=0):
         """Page-locked numpy view (N, A) [(N, A) complex128 with free_action_space] that ``step`` uploads from
@@ -543,7 +625,7 @@ class SDCVecEnv:
         (index 0 / 1) exist so a caller can fill one while the other is in flight."""
         host = self._ensure_host()
         while len(host["actions"]) <= index:
-            host["actions"].append(_torch().zeros_like(host["action"]).pin_memory())
+            host["actions"].append(_torch().zeros_like(host["actions"][0]).pin_memory())
             host["action_np"].append(host["actions"][-1].numpy())
             host["action_ptr"].append(host["actions"][-1].data_ptr())
         a = host["actions"][index].numpy()
@@ -577,6 +659,7 @@ class SDCVecEnv:
         actions, self._pending = self._pending, None
         return self.step(actions)
 
+    @_lib.on_device
     def step(self, actions):
         """(obs, rewards, dones, infos) like ``DummyVecEnv.step`` over the reference envs."""
         torch = _torch()
@@ -590,74 +673,47 @@ class SDCVecEnv:
             obs = self.observation_tensor()
             dones = (out["flags"] & _lib.FLAG_DONE).bool()
             return obs, out["reward"], dones, out
-        N, M = self.num_envs, self.M
         if self._rho_reward:
             return self._step_simple(actions)
-        host = self._ensure_host()
-        # ---- stage actions in pinned memory (no-op when the caller wrote into pinned_action_buffer()) ----
-        src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
         if self.collect_states:
+            host = self._ensure_host()
+            src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
             return self._step_collect_states(host, src)
-        chunks = self.pipeline_chunks if self.pipeline_chunks > 0 else max(1, min(8, N // 131072))
-        if self.host_pipeline == "native":
-            # ---- one C call: chunked H2D | kernels | D2H pipeline inside libsdcgym.so (csrc/hostpipe.cu) ----
-            io, hio, st, obs_dev = self._pipe_handles(host)
-            hio.action = src.data_ptr() if src is not None else None
-            _lib.check(self._L.sdcgym_pipe_step(self._pipe, ctypes.byref(self._desc), ctypes.byref(st), ctypes.byref(io),
-                                                obs_dev, ctypes.byref(hio), chunks, self._stream()),
-                       "sdcgym_pipe_step")
-            self._invalidate()
-            return self._host_outputs(host)
-        # ---- the same pipeline driven from Python with torch streams (kept as a cross-check) ----
-        bounds = [(N * c // chunks // 32 * 32 if c < chunks else N) for c in range(chunks + 1)]
-        bounds[0] = 0
-        main = torch.cuda.current_stream(self.device)
-        s_in, s_out = self._streams
-        s_in.wait_stream(main)
-        s_out.wait_stream(main)
-        a_w = self.action_dev.shape[1]
-        for c in range(chunks):
-            lo, hi = bounds[c], bounds[c + 1]
-            if hi <= lo:
-                continue
-            if self._kernel_n_act > 0:
-                with torch.cuda.stream(s_in):
-                    self.action_dev[lo:hi].copy_(src[lo:hi], non_blocking=True)
-                main.wait_stream(s_in)
-            self._launch_step(self.action_dev.data_ptr() + 8 * lo * a_w if self._kernel_n_act else None,
-                              a_w, 2 if self.free_action_space else 1, start=lo, count=hi - lo)
-            self._export_obs(self.S, lo, hi - lo)
-            s_out.wait_stream(main)
-            with torch.cuda.stream(s_out):
-                host["obs"][lo:hi].copy_(self.obs_aos[lo:hi], non_blocking=True)
-                host["reward"][lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
-                host["flags"][lo:hi].copy_(self.flags[lo:hi], non_blocking=True)
-                host["niter"][lo:hi].copy_(self.info_niter[lo:hi], non_blocking=True)
-                host["residual"][lo:hi].copy_(self.info_residual[lo:hi], non_blocking=True)
-                host["lam"][lo:hi].copy_(self.info_lam[lo:hi], non_blocking=True)
-        s_out.synchronize()
-        main.wait_stream(s_out)
-        self._invalidate()
-        return self._host_outputs(host)
+        return self._step_host(actions)
 
-    def _pipe_handles(self, host):
-        """The native host pipeline (csrc/hostpipe.cu) and its cached argument structs (io, hio, state, obs_dev)."""
+    def _block_io(self):
+        """The native host pipeline (csrc/hostpipe.cu) and its cached argument structs."""
         if self._pipe is None:
             handle = ctypes.c_void_p()
             _lib.check(self._L.sdcgym_pipe_create(64, ctypes.byref(handle)), "sdcgym_pipe_create")
             self._pipe = handle
-        if self._pipe_args is None:
-            # the device / pinned buffers never move: build the argument structs once
-            io = _lib.StepIO()
-            io.action = self.action_dev.data_ptr() if self._kernel_n_act else None
-            io.reward, io.flags = self.reward.data_ptr(), self.flags.data_ptr()
-            io.info_residual, io.info_niter = self.info_residual.data_ptr(), self.info_niter.data_ptr()
-            io.info_lam, io.terminal_obs = self.info_lam.data_ptr(), self.terminal.data_ptr()
-            hio = _lib.HostIO()
-            hio.obs, hio.reward, hio.flags = host["obs"].data_ptr(), host["reward"].data_ptr(), host["flags"].data_ptr()
-            hio.niter, hio.residual, hio.lam = host["niter"].data_ptr(), host["residual"].data_ptr(), host["lam"].data_ptr()
-            self._pipe_args = (io, hio, self._state(), self.obs_aos.data_ptr())
-        return self._pipe_args
+        if self._bio is None:
+            # the device buffers never move: build the argument structs once
+            bio = _lib.BlockIO()
+            bio.dev_block = self.dev_block.data_ptr()
+            bio.action_dev = self.action_dev.data_ptr() if self._kernel_n_act else None
+            bio.terminal_obs = self.terminal.data_ptr() if self.terminal is not None else None
+            bio.skip_u = int(self._const_u)
+            self._bio = (bio, self._state())
+        self._bio[0].chunks = self.pipeline_chunks
+        return self._bio
+
+    def _step_host(self, actions, vn=None):
+        """numpy in / numpy out as ONE C call (``sdcgym_pipe_step_block``): pinned actions -> H2D | step + export
+        kernels | D2H straight into the result block whose views are returned."""
+        host = self._ensure_host()
+        src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
+        hs, owned = self._acquire_set(host)
+        bio, st = self._block_io()
+        bio.host_block = hs.ptr
+        bio.action_host = src.data_ptr() if src is not None else None
+        _lib.check(self._L.sdcgym_pipe_step_block(self._pipe, ctypes.byref(self._desc), ctypes.byref(st),
+                                                  ctypes.byref(self._layout), ctypes.byref(bio),
+                                                  None if vn is None else ctypes.byref(vn), self._stream()),
+                   "sdcgym_pipe_step_block")
+        self._step_count += 1
+        self._invalidate()
+        return self._host_outputs(hs, owned)
 
     def _step_simple(self, actions):
         """Unpipelined host step (rarely used configurations): upload, device step, download."""
@@ -673,35 +729,50 @@ class SDCVecEnv:
         dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
         niter = out["niter"].cpu().numpy()
         infos = LazyInfos(niter, out["residual"].cpu().numpy(), out["lam"].cpu().numpy(), dones,
-                          _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]), self._fetch_terminal)
+                          _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]), self._terminal_fetcher())
         infos.flags = flags
         return obs, out["reward"].cpu().numpy(), dones, infos
 
-    def _host_outputs(self, host):
-        N = self.num_envs
-        cp = (lambda x: x) if self.reuse_buffers else np.copy
-        v = host["np"]
-        obs = cp(v["obs"])
-        rewards = cp(v["reward"])
-        flags = cp(v["flags"])
+    def _host_outputs(self, hs, owned):
+        if owned:
+            cp = lambda x: x  # noqa: E731 - the block is the caller's until they drop it (see _acquire_set)
+        else:
+            self.host_set_copies += 1
+            cp = np.ascontiguousarray if hs.obs.flags.c_contiguous else (lambda x: np.array(x, order="C"))
+        obs, rewards, flags = cp(hs.obs), cp(hs.reward), cp(hs.flags)
         dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
-        niter = cp(v["niter"])
-        lam = cp(v["lam"])
-        truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
-        infos = LazyInfos(niter, cp(v["residual"]), lam, dones, truncated_key, self._fetch_terminal)
+        niter = cp(hs.niter)
+        infos = LazyInfos(niter, cp(hs.residual), cp(hs.lam), dones, _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]),
+                          self._terminal_fetcher())
         infos.flags = flags
         return obs, rewards, dones, infos
+
+    def _terminal_fetcher(self):
+        """``info['terminal_observation']`` is served lazily from the device's terminal planes, which the NEXT step
+        overwrites: an ``infos`` object read after a later step raises instead of returning that step's data."""
+        stamp = self._step_count
+
+        def fetch():
+            if self._step_count != stamp:
+                raise RuntimeError("terminal observations of this step are gone: the env has stepped since "
+                                   "(read info['terminal_observation'] / infos.terminal_observations() before the next step)")
+            return self._fetch_terminal()
+
+        return fetch
 
     def _fetch_terminal(self):
         """terminal observations (N, 2, M) complex128 of the last step (valid rows: finished envs)."""
         torch = _torch()
         if self.collect_states:
             return self._terminal_old_states.cpu().numpy()
-        keep = self.obs_aos.clone()
-        self._export_obs(self.terminal)
-        out = torch.view_as_complex(self.obs_aos).cpu().numpy()
-        self.obs_aos.copy_(keep)
-        return out
+        if self.terminal is None:
+            raise RuntimeError("terminal observations are not kept (keep_terminal=False)")
+        with self._guard:
+            if self._term_aos is None:
+                self._term_aos = torch.empty_like(self.obs_aos)
+            _lib.check(self._L.sdcgym_export_obs(self.M, self.num_envs, self.ld, self.terminal.data_ptr(),
+                                                 self._term_aos.data_ptr(), self._stream()), "sdcgym_export_obs")
+            return torch.view_as_complex(self._term_aos).cpu().numpy()
 
     def _step_collect_states(self, host, src):
         torch = _torch()
@@ -713,6 +784,7 @@ class SDCVecEnv:
                           2 if self.free_action_space else 1)
         if self.autoreset:
             self._reset_done_envs()
+        self._step_count += 1
         self._invalidate()
         obs = torch.view_as_complex(self.old_states).cpu().numpy()
         flags = self.flags[:N].cpu().numpy()
@@ -721,11 +793,12 @@ class SDCVecEnv:
         niter = self.info_niter[:N].cpu().numpy()
         truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
         infos = LazyInfos(niter, self.info_residual[:N].cpu().numpy(), lam, dones, truncated_key,
-                          self._fetch_terminal)
+                          self._terminal_fetcher())
         infos.flags = flags
         return obs, self.reward[:N].cpu().numpy(), dones, infos
 
     # ------------------------------------------------------------------ state injection (tests, dp_playground)
+    @_lib.on_device
     def set_state(self, u, r, niter=None):
         """Overwrite (u, r) of all envs from host arrays (N, M) complex128 (the reference's ``env.state = ...``)."""
         torch = _torch()
@@ -758,12 +831,14 @@ class SDCVecEnv:
             return [None] * (self.num_envs if indices is None else len(indices))
         raise AttributeError(name)
 
+    @_lib.on_device
     def state_dict(self):
         """Checkpointable env state (device tensors cloned to host)."""
         N = self.num_envs
         return {k: getattr(self, k)[..., :N].cpu() for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr")} | {
             "seed": int(self._desc.seed)}
 
+    @_lib.on_device
     def load_state_dict(self, sd):
         N = self.num_envs
         for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
@@ -771,9 +846,10 @@ class SDCVecEnv:
         self._desc.seed = int(sd["seed"])
         self._invalidate()
 
+    @_lib.on_device
     def close(self):
         self._host = None
-        self._pipe_args = None
+        self._bio = None
         if self._pipe is not None:
             self._L.sdcgym_pipe_destroy(self._pipe)
             self._pipe = None

@@ -14,7 +14,6 @@ the same normaliser (the shift is the running mean, identical everywhere).
 from __future__ import annotations
 
 import ctypes
-import pickle
 
 import numpy as np
 
@@ -102,6 +101,7 @@ class VecNormalize:
         self._rsums = self._allsums[2 * self.P + 1:]
         self._obs_aos = torch.zeros((max(N, 1), 2, M, 2), dtype=torch.float64, device=dev)
         self.old_reward = None
+        self._guard = venv._guard
 
     # ---- delegation --------------------------------------------------------------------------------
     def __getattr__(self, name):
@@ -162,6 +162,7 @@ class VecNormalize:
         return t if v.output == "torch" else t.cpu().numpy()
 
     # ---- VecEnv API --------------------------------------------------------------------------------
+    @_lib.on_device
     def reset(self, **kw):
         v = self.venv
         v.reset(**kw)
@@ -178,6 +179,7 @@ class VecNormalize:
         self._normalize_planes(self.venv.terminal, self.norm_terminal)
         return self.norm_terminal[:, : self.venv.num_envs]
 
+    @_lib.on_device
     def step_tensor(self, actions=None, obs_out=None):
         """Device-resident normalised step.  Returns the env's dict plus ``obs_planes`` (normalised S planes),
         ``reward`` replaced by the normalised reward and ``raw_reward``; ``terminal`` (normalised terminal planes)
@@ -198,8 +200,8 @@ class VecNormalize:
             self._merge(self.obs_rms, self.P, total, self._sums)
             self._merge(self.ret_rms, 1, total, self._rsums)
         if self.norm_obs:
-            out = _StepOut(raw, self._normalized_terminal)
-            del out["terminal"]
+            out = _StepOut(raw, self._normalized_terminal if self.venv.terminal is not None else None)
+            out.pop("terminal", None)
             if self.training and not combined:
                 self._update(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
             dst = self.norm_planes
@@ -250,26 +252,25 @@ class VecNormalize:
         return vn
 
     def _native_host_step(self, actions):
-        """numpy in / numpy out through ONE C call (``sdcgym_pipe_step_vecnorm``): upload, step, statistics,
-        normalisation, packed download - the reference's training regime (8 envs behind VecNormalize) is pure
-        latency, and the call-by-call path costs ~200 us per step against ~50 us here."""
+        """numpy in / numpy out through ONE C call (``sdcgym_pipe_step_block`` with the normaliser attached): upload,
+        step, statistics, normalisation, one download - the reference's training regime (8 envs behind VecNormalize)
+        is pure latency, and the call-by-call path costs ~200 us per step against ~50 us here."""
         v = self.venv
-        host = v._ensure_host()
-        src = v._stage_actions(host, actions) if v._kernel_n_act > 0 else None
-        io, hio, st, obs_dev = v._pipe_handles(host)
-        hio.action = src.data_ptr() if src is not None else None
-        vn = self._vecnorm_struct()
-        _lib.check(self._L.sdcgym_pipe_step_vecnorm(v._pipe, ctypes.byref(v._desc), ctypes.byref(st), ctypes.byref(io),
-                                                    obs_dev, ctypes.byref(hio), ctypes.byref(vn), v._stream()),
-                   "sdcgym_pipe_step_vecnorm")
-        v._invalidate()
+        obs, rewards, dones, infos = v._step_host(actions, vn=self._vecnorm_struct())
         if self.norm_obs:
             self.current_norm_planes = self.norm_planes
         self.old_reward = v.reward[: v.num_envs]
-        obs, rewards, dones, infos = v._host_outputs(host)
-        infos._terminal_fetch = lambda: self._terminal_host(self._terminal_planes_full())
+        stamp = v._step_count
+
+        def fetch():
+            if v._step_count != stamp:
+                raise RuntimeError("terminal observations of this step are gone: the env has stepped since")
+            return self._terminal_host(self._terminal_planes_full())
+
+        infos._terminal_fetch = fetch
         return obs, rewards, dones, infos
 
+    @_lib.on_device
     def step(self, actions):
         """(obs, rewards, dones, infos) with normalised obs / rewards (numpy or torch per the env's ``output``)."""
         torch = _torch()
@@ -300,6 +301,8 @@ class VecNormalize:
         return obs, out["reward"].cpu().numpy(), dones, infos
 
     def _terminal_planes_full(self):
+        if self.venv.terminal is None:
+            raise RuntimeError("terminal observations are not kept (keep_terminal=False)")
         if not self.norm_obs:
             return self.venv.terminal
         self._normalize_planes(self.venv.terminal, self.norm_terminal)
@@ -318,6 +321,7 @@ class VecNormalize:
     def get_original_reward(self):
         return None if self.old_reward is None else self.old_reward.cpu().numpy()
 
+    @_lib.on_device
     def get_original_obs(self):
         return self._obs_out(self.venv.S)
 
@@ -329,28 +333,68 @@ class VecNormalize:
         y = np.clip((flat - mean) / np.sqrt(var + self.epsilon), -self.clip_obs, self.clip_obs)
         return y.view(np.complex128).reshape(x.shape)
 
-    # ---- persistence (SB3: VecNormalize.save / load, utils/utils.py:415-417) --------------------------------
+    # ---- persistence (SB3: VecNormalize.save / load, utils/utils.py:297,415-417) -----------------------------
+    # The reference's `--env_path` files are SB3 pickles of the wrapper object (complex (2, M) obs_rms).  They are
+    # not readable here (SB3 is not a dependency, unpickling runs arbitrary code, and the statistics kept here are
+    # per REAL plane - 4M entries - see the module docstring), so `load` rejects them with a clear message.  The own
+    # format is a versioned .npz without pickled objects.
+    FILE_FORMAT = "sdc_gym_b200.VecNormalize"
+    FILE_VERSION = 1
+
     def state_dict(self):
         return dict(obs_rms=self.obs_rms.state(), ret_rms=self.ret_rms.state(), returns=self.returns.cpu().numpy(),
                     clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
-                    norm_obs=self.norm_obs, norm_reward=self.norm_reward)
+                    norm_obs=self.norm_obs, norm_reward=self.norm_reward, training=self.training)
 
     def load_state_dict(self, sd):
         torch = _torch()
+        if not isinstance(sd, dict) or "obs_rms" not in sd or "ret_rms" not in sd:
+            raise TypeError("not a sdc_gym_b200 VecNormalize state dict (an SB3 VecNormalize object cannot be loaded: "
+                            "its statistics are complex (2, M), the device normaliser keeps 4M real planes)")
+        if np.asarray(sd["obs_rms"]["mean"]).shape != (self.P,):
+            raise ValueError(f"normaliser statistics are for {np.asarray(sd['obs_rms']['mean']).shape[0] // 4} nodes, "
+                             f"this env has M={self.P // 4}")
         self.obs_rms.load(sd["obs_rms"])
         self.ret_rms.load(sd["ret_rms"])
-        self.returns.copy_(torch.as_tensor(sd["returns"]))
-        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
-            setattr(self, k, sd[k])
+        ret = torch.as_tensor(np.asarray(sd["returns"], dtype=np.float64))
+        if ret.numel() == self.returns.numel():  # per-env running returns only make sense for the same batch
+            self.returns.copy_(ret)
+        else:
+            self.returns.zero_()
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon"):
+            setattr(self, k, float(sd[k]))
+        for k in ("norm_obs", "norm_reward", "training"):
+            if k in sd:
+                setattr(self, k, bool(sd[k]))
 
     def save(self, path):
+        sd = self.state_dict()
         with open(path, "wb") as f:
-            pickle.dump(self.state_dict(), f)
+            np.savez(f, format=np.array(self.FILE_FORMAT), version=np.array(self.FILE_VERSION),
+                     obs_mean=sd["obs_rms"]["mean"], obs_var=sd["obs_rms"]["var"], obs_count=np.array(sd["obs_rms"]["count"]),
+                     ret_mean=sd["ret_rms"]["mean"], ret_var=sd["ret_rms"]["var"], ret_count=np.array(sd["ret_rms"]["count"]),
+                     returns=sd["returns"],
+                     **{k: np.array(sd[k]) for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs",
+                                                     "norm_reward", "training")})
 
     @staticmethod
     def load(path, venv):
         with open(path, "rb") as f:
-            sd = pickle.load(f)
+            magic = f.read(2)
+        if magic != b"PK":  # not a zip container: most likely an SB3 `VecNormalize.save` pickle (utils/utils.py:297)
+            raise ValueError(f"{path}: not a sdc_gym_b200 VecNormalize file (.npz).  Pickles written by stable-baselines' "
+                             "VecNormalize.save are not supported: re-create the statistics with this wrapper "
+                             "(e.g. a dry run, rl_playground.py:58-82) and save them with VecNormalize.save")
+        with np.load(path, allow_pickle=False) as z:
+            if "format" not in z.files or str(z["format"]) != VecNormalize.FILE_FORMAT:
+                raise ValueError(f"{path}: not a sdc_gym_b200 VecNormalize file")
+            if int(z["version"]) > VecNormalize.FILE_VERSION:
+                raise ValueError(f"{path}: written by a newer version ({int(z['version'])})")
+            sd = dict(obs_rms=dict(mean=z["obs_mean"], var=z["obs_var"], count=float(z["obs_count"])),
+                      ret_rms=dict(mean=z["ret_mean"], var=z["ret_var"], count=float(z["ret_count"])),
+                      returns=z["returns"],
+                      **{k: z[k].item() for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs",
+                                                  "norm_reward", "training")})
         vn = VecNormalize(venv)
         vn.load_state_dict(sd)
         return vn

@@ -120,7 +120,7 @@ def test_pipelined_host_step_equals_device_step():
     act = rng.uniform(-1, 1, (n, 5))
     a = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, pipeline_chunks=5, **KW)
     b = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, **KW)
-    c = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, pipeline_chunks=3, host_pipeline="torch", **KW)
+    c = sdc_gym_b200.make("sdc-v0", num_envs=n, seed=2, pipeline_chunks=1, **KW)  # one transfer, caller's stream
     import torch
     oa = a.reset(); b.reset(); c.reset()
     for _ in range(2):

@@ -116,3 +116,89 @@ def test_env_construction_fails_loudly_without_cuda():
         sdc_gym_b200.make("sdc-v0", num_envs=4, M=3, dt=1.0, restol=1e-10)
     with pytest.raises(KeyError):
         sdc_gym_b200.make("sdc-v9", num_envs=4, M=3, dt=1.0, restol=1e-10)
+
+
+def test_block_layout_offsets_are_aligned_and_disjoint():
+    L = _lib.load()
+    lay = _lib.BlockLayout()
+    assert L.sdcgym_block_layout_init(5, 1000, ctypes.byref(lay)) == 0
+    sizes = dict(obs_u=1000 * 80, reward=8000, residual=8000, lam=16000, niter=4000, flags=1000, obs_r=1000 * 80)
+    order = ["obs_u", "reward", "residual", "lam", "niter", "flags", "obs_r"]
+    end = 0
+    for k in order:
+        off = getattr(lay, k)
+        assert off % 256 == 0 and off >= end, k
+        end = off + sizes[k]
+    assert lay.total >= end and lay.total % 256 == 0 and lay.N == 1000 and lay.M == 5
+    # skip_u transfers the contiguous tail [reward, total): everything but the u rows
+    assert lay.obs_u == 0 and lay.obs_r > lay.flags
+    assert L.sdcgym_block_layout_init(5, 0, ctypes.byref(lay)) == 0 and lay.total == 0
+    assert L.sdcgym_block_layout_init(12, 4, ctypes.byref(lay)) == -1
+    assert L.sdcgym_block_layout_init(5, 4, None) == -3
+    assert L.sdcgym_pipe_step_block(None, None, None, None, None, None, None) == -3
+
+
+def test_host_result_set_is_reused_only_when_the_caller_let_go():
+    """ownership without copies: a result block is written again only when no array handed out from it (nor any view
+    derived from one) is referenced outside the env (vec_env._HostSet)"""
+    import torch
+    from sdc_gym_b200.vec_env import LazyInfos, _HostSet
+
+    class FakeTorch:  # page-locked allocation needs CUDA; the logic under test does not
+        uint8 = torch.uint8
+
+        @staticmethod
+        def zeros(n, dtype, pin_memory):
+            return torch.zeros(n, dtype=dtype)
+
+    L = _lib.load()
+    lay = _lib.BlockLayout()
+    N, M = 37, 5
+    assert L.sdcgym_block_layout_init(M, N, ctypes.byref(lay)) == 0
+    hs = _HostSet(FakeTorch, lay, N, M, True)
+    assert hs.free() and hs.obs.shape == (N, 2, M) and hs.obs.dtype == np.complex128
+    assert np.all(hs.obs[:, 0] == 1.0) and np.all(hs.obs[:, 1] == 0.0)
+    hs.root[lay.obs_r: lay.obs_r + 16].view(np.complex128)[0] = 2 + 3j  # what the DMA writes
+    assert hs.obs[0, 1, 0] == 2 + 3j and hs.free()
+    for make_ref in (lambda: hs.obs, lambda: hs.obs[3], lambda: hs.reward[2:4], lambda: hs.lam.real,
+                     lambda: LazyInfos(hs.niter, hs.residual, hs.lam, np.ones(N, bool), None, None),
+                     lambda: torch.from_numpy(hs.obs), lambda: hs.flags.view(np.bool_)):
+        ref = make_ref()
+        assert not hs.free()
+        del ref
+        assert hs.free()
+    copy = np.ascontiguousarray(hs.obs)  # a real copy does not pin the block
+    assert hs.free() and copy.flags.c_contiguous
+    hs0 = _HostSet(FakeTorch, lay, N, M, False)
+    assert np.all(hs0.obs == 0)
+
+
+def test_vecnormalize_load_rejects_foreign_files(tmp_path):
+    import pickle
+
+    from sdc_gym_b200.vec_normalize import VecNormalize
+
+    p = tmp_path / "vecnormalize.pkl"
+    with open(p, "wb") as f:
+        pickle.dump({"obs_rms": "whatever an SB3 pickle holds"}, f)
+    with pytest.raises(ValueError, match="stable-baselines"):
+        VecNormalize.load(str(p), None)  # rejected before anything is unpickled or any device is touched
+    q = tmp_path / "other.npz"
+    np.savez(q, a=np.zeros(3))
+    with pytest.raises(ValueError, match="not a sdc_gym_b200"):
+        VecNormalize.load(str(q), None)
+
+
+def test_register_gym_is_a_noop_without_gym():
+    import importlib.util
+
+    import sdc_gym_b200
+
+    ids = sdc_gym_b200.register_gym()
+    if importlib.util.find_spec("gym") is None and importlib.util.find_spec("gymnasium") is None:
+        assert ids == []
+    else:
+        assert all(i.split(":")[1] in sdc_gym_b200.REGISTRY for i in ids)
+    from sdc_gym_b200 import gym_adapter
+
+    assert callable(gym_adapter.make_single)
