@@ -7,7 +7,10 @@
 // streams and events.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -371,6 +374,28 @@ extern "C" int sdcgym_block_layout_init(int M, int64_t N, sdcgym_block_layout* L
 }
 
 namespace {
+// SDCGYM_PIPE_TRACE=1: time stamps (CUDA events) of every stage of one chunked step, printed to stderr - the tool behind
+// the chunk schedule (tools/e2e_sweep.py); off by default, costs nothing then
+struct PipeTrace {
+    bool on = false;
+    cudaEvent_t start{}, h2d[64], k[64], d2h[64], small[64];
+    PipeTrace() {
+        const char* e = getenv("SDCGYM_PIPE_TRACE");
+        on = e && e[0] == '1';
+    }
+    void init() {
+        if (!on || start) return;
+        cudaEventCreate(&start);
+        for (int c = 0; c < 64; c++) {
+            cudaEventCreate(&h2d[c]);
+            cudaEventCreate(&k[c]);
+            cudaEventCreate(&d2h[c]);
+            cudaEventCreate(&small[c]);
+        }
+    }
+};
+PipeTrace g_trace;
+
 // the pipe's streams, events and staging belong to the device it was created on: make that device current for the call
 struct DeviceScope {
     int prev = -1;
@@ -387,6 +412,23 @@ struct DeviceScope {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// Wait for a stream by polling: cudaStreamSynchronize may block on an interrupt (tens of microseconds of wake-up
+// latency per call); a step is a few milliseconds at most, so the calling thread spins instead.
+inline cudaError_t spin_sync(cudaStream_t s) {
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(s);
+        if (e != cudaErrorNotReady) return e;
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
+inline double host_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
 
 int auto_chunks(int64_t N) {
     // one transfer up to 32 k envs (<= ~4 MB of results: the copy is shorter than the extra launches and events of a
@@ -465,11 +507,18 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
         PIPE_CHECK(cudaMemcpyAsync(hb + first, db + first, L->total - first, cudaMemcpyDeviceToHost, cs));
         if (vn)  // the host sees the normalised reward; the device block keeps the raw one
             PIPE_CHECK(cudaMemcpyAsync(hb + L->reward, vn->out_reward, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, cs));
-        PIPE_CHECK(cudaStreamSynchronize(cs));
+        PIPE_CHECK(spin_sync(cs));
         return 0;
     }
 
     // ---- large batch: H2D(actions) | step + export kernels | D2H(results), chunk by chunk over four streams ----
+    const bool trace = g_trace.on && chunks <= 64;
+    bool small_sent[64] = {false};
+    const double t_enter = trace ? host_ms() : 0.0;
+    if (trace) {
+        g_trace.init();
+        cudaEventRecord(g_trace.start, cs);
+    }
     PIPE_CHECK(cudaEventRecord(p->ev_start, cs));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
     PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_start, 0));
@@ -486,6 +535,7 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
                                        cudaMemcpyHostToDevice, p->s_in));
             PIPE_CHECK(cudaEventRecord(p->ev_in[c], p->s_in));
             PIPE_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[c], 0));
+            if (trace) cudaEventRecord(g_trace.h2d[c], p->s_in);
         }
         sdcgym_state s2 = *st;
         s2.N = n;
@@ -510,11 +560,13 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
         if (rc) return rc;
         PIPE_CHECK(cudaEventRecord(p->ev_k[c], p->s_k));
         PIPE_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[c], 0));
+        if (trace) cudaEventRecord(g_trace.k[c], p->s_k);
 #define SEG(strm, off, from, count, bytes_per_env)                                                         \
     PIPE_CHECK(cudaMemcpyAsync(hb + (off) + (size_t)(from) * (bytes_per_env), db + (off) + (size_t)(from) * (bytes_per_env), \
                                (size_t)(count) * (bytes_per_env), cudaMemcpyDeviceToHost, strm));
         SEG(p->s_out, L->obs_r, lo, n, row_bytes)
         if (!skip_u) SEG(p->s_out, L->obs_u, lo, n, row_bytes)
+        if (trace) cudaEventRecord(g_trace.d2h[c], p->s_out);
         if ((c + 1) % group == 0 || c + 1 == chunks) {
             PIPE_CHECK(cudaStreamWaitEvent(p->s_out2, p->ev_k[c], 0));
             const int64_t sn = hi - small_lo;
@@ -524,11 +576,32 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
             SEG(p->s_out2, L->residual, small_lo, sn, sizeof(double))
             SEG(p->s_out2, L->lam, small_lo, sn, 2 * sizeof(double))
             small_lo = hi;
+            if (trace) {
+                cudaEventRecord(g_trace.small[c], p->s_out2);
+                small_sent[c] = true;
+            }
         }
 #undef SEG
     }
-    PIPE_CHECK(cudaStreamSynchronize(p->s_out));
-    PIPE_CHECK(cudaStreamSynchronize(p->s_out2));
+    const double t_issued = trace ? host_ms() : 0.0;
+    PIPE_CHECK(spin_sync(p->s_out));
+    PIPE_CHECK(spin_sync(p->s_out2));
+    if (trace) {
+        fprintf(stderr, "[sdcgym pipe] N=%lld chunks=%d  host: all work issued after %.3f ms, streams drained after %.3f ms"
+                        "  (device time stamps, ms after the call started: actions on device | kernels done | "
+                        "observation rows on host | small arrays on host)\n", (long long)N, chunks, t_issued - t_enter,
+                host_ms() - t_enter);
+        for (int c = 0; c < chunks; c++) {
+            const int64_t lo = chunk_begin(N, c, chunks), hi = chunk_begin(N, c + 1, chunks);
+            if (hi <= lo) continue;
+            float a = -1.f, b = -1.f, d = -1.f, e = -1.f;
+            if (A > 0) cudaEventElapsedTime(&a, g_trace.start, g_trace.h2d[c]);
+            cudaEventElapsedTime(&b, g_trace.start, g_trace.k[c]);
+            cudaEventElapsedTime(&d, g_trace.start, g_trace.d2h[c]);
+            if (small_sent[c]) cudaEventElapsedTime(&e, g_trace.start, g_trace.small[c]);
+            fprintf(stderr, "  chunk %2d envs %8lld  %7.3f | %7.3f | %7.3f | %7.3f\n", c, (long long)(hi - lo), a, b, d, e);
+        }
+    }
     PIPE_CHECK(cudaEventRecord(p->ev_start, p->s_k));
     PIPE_CHECK(cudaStreamWaitEvent(cs, p->ev_start, 0));
     return 0;

@@ -117,8 +117,10 @@ class _HostSet:
         self.lam = seg(layout.lam, N * 16, np.complex128)
         self.niter = seg(layout.niter, N * 4, np.int32)
         self.flags = seg(layout.flags, N, np.uint8)
+        self._done_u8 = np.zeros(N, np.uint8)  # `dones`, derived from the flags on the host (not part of the block)
+        self.dones = self._done_u8.view(np.bool_)
         del u_rows, root
-        self._handed = (self.obs, self.reward, self.residual, self.lam, self.niter, self.flags)
+        self._handed = (self.obs, self.reward, self.residual, self.lam, self.niter, self.flags, self._done_u8, self.dones)
         self._baseline = self._counts()
 
     def _counts(self):
@@ -591,6 +593,10 @@ class SDCVecEnv:
             act = torch.zeros((self.num_envs, self.action_dev.shape[1]), dtype=torch.float64, pin_memory=True)
             # numpy views / pointers are built once: tensor.numpy() per step would cost more than a small batch's kernels
             self._host = dict(actions=[act], action_np=[act.numpy()], action_ptr=[act.data_ptr()], sets=[], spill=None)
+            # page-locked allocation costs ~0.5 ms per MB: take the blocks the usual loop ping-pongs between now, not
+            # inside somebody's second step
+            for _ in range(1 if self.reuse_buffers else min(2, self.max_host_sets)):
+                self._host["sets"].append(self._new_set())
         return self._host
 
     def _new_set(self):
@@ -740,7 +746,11 @@ class SDCVecEnv:
             self.host_set_copies += 1
             cp = np.ascontiguousarray if hs.obs.flags.c_contiguous else (lambda x: np.array(x, order="C"))
         obs, rewards, flags = cp(hs.obs), cp(hs.reward), cp(hs.flags)
-        dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
+        if owned:  # no per-step allocation: the mask lands in the block's own `dones` array
+            np.bitwise_and(flags, _lib.FLAG_DONE, out=hs._done_u8)
+            dones = hs.dones
+        else:
+            dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
         niter = cp(hs.niter)
         infos = LazyInfos(niter, cp(hs.residual), cp(hs.lam), dones, _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]),
                           self._terminal_fetcher())

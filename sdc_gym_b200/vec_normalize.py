@@ -346,7 +346,10 @@ class VecNormalize:
                     clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
                     norm_obs=self.norm_obs, norm_reward=self.norm_reward, training=self.training)
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, restore_flags=False):
+        """statistics, returns and hyper-parameters; ``restore_flags`` also restores norm_obs / norm_reward / training
+        (what ``VecNormalize.load`` does - a file resumes the wrapper as it was saved; an explicit
+        ``load_state_dict`` into an object the caller configured keeps the caller's flags)"""
         torch = _torch()
         if not isinstance(sd, dict) or "obs_rms" not in sd or "ret_rms" not in sd:
             raise TypeError("not a sdc_gym_b200 VecNormalize state dict (an SB3 VecNormalize object cannot be loaded: "
@@ -363,9 +366,10 @@ class VecNormalize:
             self.returns.zero_()
         for k in ("clip_obs", "clip_reward", "gamma", "epsilon"):
             setattr(self, k, float(sd[k]))
-        for k in ("norm_obs", "norm_reward", "training"):
-            if k in sd:
-                setattr(self, k, bool(sd[k]))
+        if restore_flags:
+            for k in ("norm_obs", "norm_reward", "training"):
+                if k in sd:
+                    setattr(self, k, bool(sd[k]))
 
     def save(self, path):
         sd = self.state_dict()
@@ -396,7 +400,7 @@ class VecNormalize:
                       **{k: z[k].item() for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs",
                                                   "norm_reward", "training")})
         vn = VecNormalize(venv)
-        vn.load_state_dict(sd)
+        vn.load_state_dict(sd, restore_flags=True)
         return vn
 
     def close(self):

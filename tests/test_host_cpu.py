@@ -162,7 +162,8 @@ def test_host_result_set_is_reused_only_when_the_caller_let_go():
     assert hs.obs[0, 1, 0] == 2 + 3j and hs.free()
     for make_ref in (lambda: hs.obs, lambda: hs.obs[3], lambda: hs.reward[2:4], lambda: hs.lam.real,
                      lambda: LazyInfos(hs.niter, hs.residual, hs.lam, np.ones(N, bool), None, None),
-                     lambda: torch.from_numpy(hs.obs), lambda: hs.flags.view(np.bool_)):
+                     lambda: torch.from_numpy(hs.obs), lambda: hs.flags.view(np.bool_), lambda: hs.dones,
+                     lambda: hs.dones[1:3]):
         ref = make_ref()
         assert not hs.free()
         del ref
