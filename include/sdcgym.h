@@ -37,8 +37,9 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 4 /* 4: result blocks (sdcgym_block_*, sdcgym_pipe_step_block), sdcgym_export_rows */
+#define SDCGYM_ABI_VERSION 5 /* 5: sweep_mode (certified substitution sweeps) + its work buffers in sdcgym_state */
 #define SDCGYM_MAX_M 9
+#define SDCGYM_CERT_PLANES 8
 
 /* error codes (negative); positive return values are cudaError_t */
 #define SDCGYM_EINVAL (-1)       /* bad argument value */
@@ -77,6 +78,19 @@ extern "C" {
 #define SDCGYM_ACTION_F32 2   /* use_doubles=False: Q_delta entries are stored in the float32/complex64 action
                                * dtype (sdc_env.py:100,109,138-140): the scaled action is rounded to float32 */
 
+/* sweep_mode: how the sdc-v0 full solve iterates (sdc_env.py:224-247)
+ *   EXACT      the reference's numpy/OpenBLAS rounding sequence, operation for operation: every output bit-equal.
+ *   CERTIFIED  substitution sweeps  u+ = u + Pinv r,  r+ = u0 - u+ + z (Q u+)  with the real collocation matrix (the
+ *              node-by-node form of sdc_env_nonlinear.py:248-264; about half the FP64 instructions, and no
+ *              np.linalg.inv emulation).  Each `nr > 100 nr_old` / `nr < restol` decision is taken with a rigorous
+ *              running bound on |nr - nr_reference| (csrc/certify.cuh); envs that meet a decision inside the bound are
+ *              re-run by the exact kernel.  niter / done / converged / err are bit-equal to the reference for EVERY env;
+ *              u, r, ||r||, reward agree within rounding (<= 1e-12 relative).  Applies to sdc-v0 steps that start from
+ *              an exact state (after reset / auto-reset); combinations without a certificate (sdc-v1, collect_states)
+ *              run the exact kernel.  Needs the work buffers of sdcgym_state. */
+#define SDCGYM_SWEEP_EXACT 0
+#define SDCGYM_SWEEP_CERTIFIED 1
+
 /* OpenBLAS core whose rounding sequence is reproduced */
 #define SDCGYM_BLAS_SKYLAKEX 0
 #define SDCGYM_BLAS_HASWELL 1
@@ -93,6 +107,8 @@ typedef struct sdcgym_env_desc {
     int32_t blas_variant;      /* SDCGYM_BLAS_* */
     int32_t autoreset;         /* DummyVecEnv semantics: a finished env is reset inside the step */
     int32_t curriculum;        /* lambda_real_interpolation_interval given (sdc_env.py:287-292) */
+    int32_t sweep_mode;        /* SDCGYM_SWEEP_* */
+    int32_t reserved0;
     double dt, restol, step_penalty, residual_weight, norm_factor;
     double lam_re_lo, lam_re_hi, lam_im_lo, lam_im_hi; /* lambda sampling box */
     double interp_x0, interp_x1;                       /* curriculum episode interval */
@@ -111,6 +127,10 @@ typedef struct sdcgym_state {
     int32_t* niter;    /* [ld] */
     int32_t* episodes; /* [ld]  num_episodes (sdc_env.py:81,276) */
     uint32_t* rng_ctr; /* [ld]  number of lambda draws made so far */
+    /* work buffers of SDCGYM_SWEEP_CERTIFIED (NULL otherwise): */
+    float* cert;            /* [SDCGYM_CERT_PLANES][ld] per-env certificate constants, rewritten by every step */
+    int32_t* fallback_list; /* [N] indices of the envs the exact kernel re-ran in the last step */
+    int32_t* fallback_count; /* [2]: length of fallback_list for the last step, cumulative count over all steps */
 } sdcgym_state;
 
 /* Per-step inputs/outputs (device pointers; NULL outputs are skipped). */

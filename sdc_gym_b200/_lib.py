@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
 
 MAX_M = 9
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -27,6 +27,8 @@ REWARD_STRATEGIES = {
 FLAG_DONE, FLAG_CONVERGED, FLAG_ERR = 1, 2, 4
 BLAS_SKYLAKEX, BLAS_HASWELL = 0, 1
 ACTION_SCALE, ACTION_F32 = 1, 2  # bits of EnvDesc.do_scale (include/sdcgym.h)
+SWEEP_MODES = {"exact": 0, "certified": 1}
+CERT_PLANES = 8
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 
@@ -45,6 +47,8 @@ class EnvDesc(ctypes.Structure):
         ("blas_variant", ctypes.c_int32),
         ("autoreset", ctypes.c_int32),
         ("curriculum", ctypes.c_int32),
+        ("sweep_mode", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
         ("dt", ctypes.c_double),
         ("restol", ctypes.c_double),
         ("step_penalty", ctypes.c_double),
@@ -75,6 +79,9 @@ class State(ctypes.Structure):
         ("niter", ctypes.c_void_p),
         ("episodes", ctypes.c_void_p),
         ("rng_ctr", ctypes.c_void_p),
+        ("cert", ctypes.c_void_p),
+        ("fallback_list", ctypes.c_void_p),
+        ("fallback_count", ctypes.c_void_p),
     ]
 
 

@@ -177,6 +177,10 @@ extern "C" int sdcgym_step(const sdcgym_env_desc* d, const sdcgym_state* st, con
         return SDCGYM_EUNSUPPORTED;  // 'spectral_radius' reward: compose sdcgym_spectral_radius on the host side
     if (d->prec_type != SDCGYM_PREC_FIXED && st->N > 0 && !io->action) return SDCGYM_ENULL;
     if (io->old_states && d->autoreset) return SDCGYM_EINVAL;  // collect_states: reset is a separate call
+    if (d->sweep_mode != SDCGYM_SWEEP_EXACT && d->sweep_mode != SDCGYM_SWEEP_CERTIFIED) return SDCGYM_EINVAL;
+    if (d->sweep_mode == SDCGYM_SWEEP_CERTIFIED && st->N > 0 && (!st->cert || !st->fallback_list || !st->fallback_count))
+        return SDCGYM_ENULL;
+    if (d->sweep_mode == SDCGYM_SWEEP_CERTIFIED && st->N > INT32_MAX) return SDCGYM_EINVAL;  // int32 fallback list
     switch (d->M) {
 #define C(m) case m: return sdcgym_launch_step_m##m(d, st, io, stream);
         C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9)

@@ -6,6 +6,7 @@
 
 #include "step_params.cuh"
 #include "team_kernels.cuh"
+#include "fast_kernels.cuh"
 
 #ifndef SDCGYM_M
 #error "compile with -DSDCGYM_M=<2..9>"
@@ -57,6 +58,46 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// opt-in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute, remembered per (instantiation, device)
+template <typename K>
+static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& configured) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = (dev >= 0 && dev < 64) ? (uint64_t(1) << dev) : 0;
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
+}
+
+// SDCGYM_SWEEP_CERTIFIED, diagonal Q_delta, sdc-v0: certificate -> substitution sweeps -> exact kernel over the
+// fallback list (fast_kernels.cuh).  Three launches on the caller's stream.
+template <int V>
+static cudaError_t launch_certified_diag(const StepParams<kM>& p, const FastWork& fw, cudaStream_t s) {
+    cert_kernel<kM, V><<<(unsigned)((p.N + kCertBlock - 1) / kCertBlock), kCertBlock, 0, s>>>(p, fw);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    constexpr int fminb = (kM <= 5) ? 4 : ((kM <= 7) ? 3 : 2);
+    fast_step_kernel<kM, V, fminb><<<(unsigned)((p.N + kFastBlock - 1) / kFastBlock), kFastBlock, 0, s>>>(p, fw);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    constexpr int hold = kHoldDiag, minb = HoldPolicy<kM>::diag_minb, block = HoldPolicy<kM>::diag_block;
+    constexpr size_t smem = step_kernel_smem_bytes<kM, hold, block>();
+    auto kernel = step_list_kernel<kM, V, hold, minb, block>;
+    static std::atomic<uint64_t> configured{0};
+    e = opt_in_smem(kernel, smem, configured);
+    if (e != cudaSuccess) return e;
+    // a fixed grid (the list is short and its length lives on the device): grid-stride over the list
+    const int64_t want = (p.N / 16 + block - 1) / block;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+    kernel<<<grid, block, smem, s>>>(p, fw);
+    return cudaGetLastError();
+}
+
 }  // namespace sdcgym
 
 using namespace sdcgym;
@@ -95,6 +136,11 @@ extern "C" int SDCGYM_CAT(sdcgym_launch_step_m, SDCGYM_M)(const sdcgym_env_desc*
     const bool full = d->env_kind == SDCGYM_ENV_FULL;
     const bool skx = d->blas_variant == SDCGYM_BLAS_SKYLAKEX;
     cudaError_t e;
+    if (d->sweep_mode == SDCGYM_SWEEP_CERTIFIED && full && !dense && io->old_states == nullptr) {
+        FastWork fw{st->cert, st->fallback_list, st->fallback_count};
+        e = skx ? launch_certified_diag<0>(p, fw, s) : launch_certified_diag<1>(p, fw, s);
+        return (int)e;
+    }
 #define SDCGYM_DISPATCH(KIND, V, DENSE) e = launch_step<KIND, V, DENSE>(p, s)
     if (full) {
         if (skx) { if (dense) SDCGYM_DISPATCH(SDCGYM_ENV_FULL, 0, true); else SDCGYM_DISPATCH(SDCGYM_ENV_FULL, 0, false); }

@@ -234,6 +234,7 @@ class SDCVecEnv:
         host_pipeline: str = "native",
         max_host_sets: int = 4,
         keep_terminal: bool = True,
+        sweep_mode: str = "exact",
     ):
         torch = _torch()
         if envname not in _lib.ENV_KINDS:
@@ -319,6 +320,17 @@ class SDCVecEnv:
             self.action_dev = torch.zeros((N, a_w), dtype=f64, device=dev)
             self.old_states = (torch.zeros((N, 2 * self.M, self.max_iters, 2), dtype=f64, device=dev)
                                if collect_states else None)
+            # sweep_mode='certified' (sdc-v0): substitution sweeps + per-env certificate, exact kernel for the envs whose
+            # decisions fall inside the error bound (include/sdcgym.h SDCGYM_SWEEP_CERTIFIED)
+            if sweep_mode not in _lib.SWEEP_MODES:
+                raise ValueError(f"sweep_mode must be one of {sorted(_lib.SWEEP_MODES)}")
+            self.sweep_mode = sweep_mode
+            self._certified = sweep_mode == "certified" and envname == "sdc-v0" and not collect_states
+            if self._certified:
+                self.cert = torch.zeros((_lib.CERT_PLANES, self.ld), dtype=torch.float32, device=dev)
+                self.fallback_list = torch.zeros(max(1, N), dtype=torch.int32, device=dev)
+                self.fallback_count = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._state_exact = True  # the stored (u, r) are bit-equal to the reference's (reset / exact step / injected)
         self._host = None  # pinned staging, allocated on first numpy-mode step
         self._snap = None
         self._init_res = None
@@ -352,6 +364,7 @@ class SDCVecEnv:
         d.blas_variant = detect_blas_variant() if blas_variant is None else int(blas_variant)
         d.autoreset = int(self.autoreset and not self.collect_states)
         d.curriculum = int(lambda_real_interpolation_interval is not None)
+        d.sweep_mode = _lib.SWEEP_MODES["certified" if self._certified else "exact"]
         d.dt, d.restol = self.dt, self.restol
         d.step_penalty, d.residual_weight, d.norm_factor = float(step_penalty), float(residual_weight), float(norm_factor)
         d.lam_re_lo, d.lam_re_hi = float(lambda_real_interval[0]), float(lambda_real_interval[1])
@@ -388,6 +401,10 @@ class SDCVecEnv:
         st.niter = self.niter.data_ptr() + 4 * start
         st.episodes = self.episodes.data_ptr() + 4 * start
         st.rng_ctr = self.rng_ctr.data_ptr() + 4 * start
+        if self._certified:
+            st.cert = self.cert.data_ptr() + 4 * start
+            st.fallback_list = self.fallback_list.data_ptr() + 4 * start
+            st.fallback_count = self.fallback_count.data_ptr()
         return st
 
     def _desc_for(self, start):
@@ -401,6 +418,27 @@ class SDCVecEnv:
     def _invalidate(self):
         self._snap = None
         self._init_res = None
+
+    def _certified_step_begins(self):
+        """The certificate of sweep_mode='certified' compares against a reference that starts from the SAME bits: a
+        step may only start from an exact state (reset, auto-reset, set_state), never from the rounding-level
+        approximation a previous certified step left behind (possible only with autoreset=False)."""
+        if not self._certified:
+            return
+        if not self._state_exact:
+            raise _lib.SdcGymError("sweep_mode='certified': this step would start from the result of a previous "
+                                   "certified step (autoreset=False); call reset() / set_state() first or use "
+                                   "sweep_mode='exact'")
+        if not self._desc.autoreset:
+            self._state_exact = False
+
+    def fallback_stats(self):
+        """sweep_mode='certified': (envs re-run by the exact kernel in the last step [last chunk of a pipelined host
+        step], cumulative number over all steps).  Synchronises."""
+        if not self._certified:
+            return 0, 0
+        c = self.fallback_count.cpu().numpy()
+        return int(c[0]), int(c[1])
 
     # ------------------------------------------------------------------ reset / seed
     @_lib.on_device
@@ -443,6 +481,8 @@ class SDCVecEnv:
         os_ptr = self.old_states.data_ptr() if self.old_states is not None else None
         _lib.check(self._L.sdcgym_reset(ctypes.byref(self._desc), ctypes.byref(st), lam_ptr, mask_ptr, os_ptr,
                                         self._stream()), "sdcgym_reset")
+        if mask is None:
+            self._state_exact = True
         self._invalidate()
         return self._observation()
 
@@ -515,6 +555,7 @@ class SDCVecEnv:
                          if self.old_states is not None else None)
         st = self._state(start, count)
         d = self._desc_for(start)
+        self._certified_step_begins()
         _lib.check(self._L.sdcgym_step(ctypes.byref(d), ctypes.byref(st), ctypes.byref(io), self._stream()),
                    "sdcgym_step")
 
@@ -713,6 +754,7 @@ class SDCVecEnv:
         bio, st = self._block_io()
         bio.host_block = hs.ptr
         bio.action_host = src.data_ptr() if src is not None else None
+        self._certified_step_begins()
         _lib.check(self._L.sdcgym_pipe_step_block(self._pipe, ctypes.byref(self._desc), ctypes.byref(st),
                                                   ctypes.byref(self._layout), ctypes.byref(bio),
                                                   None if vn is None else ctypes.byref(vn), self._stream()),
@@ -822,6 +864,7 @@ class SDCVecEnv:
         if niter is not None:
             self.niter[:N] = torch.as_tensor(np.asarray(niter, dtype=np.int32)).to(self.device)
         torch.cuda.current_stream(self.device).synchronize()  # `t` must outlive the kernels
+        self._state_exact = True
         self._invalidate()
 
     # ------------------------------------------------------------------ VecEnv odds and ends

@@ -63,6 +63,7 @@ int main(int argc, char** argv) {
     memcpy(d.Q, Q, sizeof Q);
 
     sdcgym_state st;
+    memset(&st, 0, sizeof st);
     st.N = N; st.ld = ld;
     CK(cudaMalloc((void**)&st.lam, 2 * ld * 8)); CK(cudaMalloc((void**)&st.S, 4 * M * ld * 8));
     CK(cudaMalloc((void**)&st.resnorm, ld * 8)); CK(cudaMalloc((void**)&st.niter, ld * 4));

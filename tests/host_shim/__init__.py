@@ -46,6 +46,7 @@ def shim():
         L.shim_step_hold5.argtypes = L.shim_step.argtypes
         L.shim_step_hold9.argtypes = L.shim_step.argtypes
         L.shim_spectral_radius.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64, vp, vp, vp]
+        L.shim_step_certified.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int]
         _shim = L
     return _shim
 
@@ -96,12 +97,19 @@ class ShimBatch:
         self.info_lam = np.zeros((ld, 2))
         self.term = np.zeros((4 * M, ld))
         self.old_states = np.zeros((n, 2 * M, 50), np.complex128) if collect else None
+        # work buffers of the certified sweep mode
+        self.cert = np.zeros((_lib.CERT_PLANES, ld), np.float32)
+        self.fallback_list = np.zeros(max(1, n), np.int32)
+        self.fallback_count = np.zeros(2, np.int32)
+        self.trace = None
 
     def _state(self):
         st = _lib.State()
         st.N, st.ld = self.n, self.ld
         for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
             setattr(st, k, getattr(self, k).ctypes.data)
+        st.cert, st.fallback_list = self.cert.ctypes.data, self.fallback_list.ctypes.data
+        st.fallback_count = self.fallback_count.ctypes.data
         return st
 
     def reset(self, lam=None, mask=None):
@@ -139,7 +147,13 @@ class ShimBatch:
         io.info_residual, io.info_niter = self.info_res.ctypes.data, self.info_niter.ctypes.data
         io.info_lam, io.terminal_obs = self.info_lam.ctypes.data, self.term.ctypes.data
         io.old_states = None if self.old_states is None else self.old_states.ctypes.data
-        rc = getattr(shim(), self.entry)(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
+        if self.entry == "shim_step_certified":
+            # trace[i, k] = (r~_k (2M doubles), ||r~_k||, margin_k) of sweep k+1 of env i
+            self.trace = np.full((self.n, self.d.max_iters, 2 * self.M + 2), np.nan)
+            rc = shim().shim_step_certified(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io),
+                                            self.trace.ctypes.data, int(getattr(self, "run_fallback", True)))
+        else:
+            rc = getattr(shim(), self.entry)(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
         assert rc == 0
         n = self.n
         f = self.flags[:n]

@@ -236,3 +236,56 @@ extern "C" int shim_spectral_radius_grad(const sdcgym_rho_desc* d, int64_t N, co
     }
     return -2;
 }
+
+// ---- certified substitution sweep mode (fast_kernels.cuh): certificate + fast step (+ per-sweep trace of r~ and the
+//      margin for the bound-dominance property test) + the exact kernel over the fallback list ----
+#include "../../sdc_gym_b200/csrc/fast_kernels.cuh"
+
+template <int M>
+static int step_certified_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io, double* trace,
+                            int run_fallback) {
+    StepParams<M> p;
+    fill_params<M>(p, d, st);
+    fill_step_io<M>(p, io);
+    FastWork fw{st->cert, st->fallback_list, st->fallback_count};
+    fw.count[0] = 0;
+    const int64_t nthreads = (p.N + kBlock - 1) / kBlock * kBlock;
+    for (int64_t i = 0; i < p.N; i++) {
+        if (d->blas_variant == 0) cert_one<M, 0>(p, fw, i);
+        else cert_one<M, 1>(p, fw, i);
+    }
+    const size_t tstride = (size_t)d->max_iters * (2 * M + 2);
+    for (int64_t i = 0; i < nthreads; i++) {
+        double* t = (trace && i < p.N) ? trace + (size_t)i * tstride : nullptr;
+        if (d->blas_variant == 0) fast_step_one<M, 0, true>(p, fw, i, t);
+        else fast_step_one<M, 1, true>(p, fw, i, t);
+    }
+    if (run_fallback) {
+        constexpr int HD = HoldPolicy<M>::diag;
+        double side[4 * M * M];
+        cplx pside[2 * 2 * M * M];
+        const int count = fw.count[0];
+        fw.count[1] += count;
+        for (int t = 0; t < count; t++) {
+            const int64_t idx = fw.list[t];
+            if (d->blas_variant == 0) step_one<M, 0, 0, false, HD>(p, idx, side, 2, pside, 2);
+            else step_one<M, 0, 1, false, HD>(p, idx, side, 2, pside, 2);
+        }
+    }
+    return 0;
+}
+
+extern "C" int shim_step_certified(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io,
+                                   double* trace, int run_fallback) {
+    switch (d->M) {
+    case 2: return step_certified_m<2>(d, st, io, trace, run_fallback);
+    case 3: return step_certified_m<3>(d, st, io, trace, run_fallback);
+    case 4: return step_certified_m<4>(d, st, io, trace, run_fallback);
+    case 5: return step_certified_m<5>(d, st, io, trace, run_fallback);
+    case 6: return step_certified_m<6>(d, st, io, trace, run_fallback);
+    case 7: return step_certified_m<7>(d, st, io, trace, run_fallback);
+    case 8: return step_certified_m<8>(d, st, io, trace, run_fallback);
+    case 9: return step_certified_m<9>(d, st, io, trace, run_fallback);
+    }
+    return -2;
+}
