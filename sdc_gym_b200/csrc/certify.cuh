@@ -35,9 +35,10 @@ SDCGYM_HD float cert_inf() { return (float)INFINITY; }
 // fp32 modulus, rounded up generously: s * rsqrt(s) with the 2-ulp hardware reciprocal square root on the device
 // (relative error < 5e-7 in total), correctly rounded sqrtf on the host build
 SDCGYM_HD float cabs_up(float re, float im) {
-    const float s = fmaf(re, re, im * im);
+    // the 1e-36 keeps s > 0 (no guard needed; it only raises the bound) and is far below anything that matters
+    const float s = fmaf(re, re, fmaf(im, im, 1e-36f));
 #ifdef __CUDA_ARCH__
-    return (s > 0.0f) ? s * rsqrtf(s) * 1.000002f : 0.0f;  // (s = +Inf gives NaN: the certificate is then unusable, as it must be)
+    return s * rsqrtf(s) * 1.000002f;  // (s = +Inf gives NaN: the certificate is then unusable, as it must be)
 #else
     return sqrtf(s) * 1.000002f;
 #endif
@@ -166,7 +167,9 @@ SDCGYM_HD void cert_envelope(const float (&Kr)[M * M], const float (&Ki)[M * M],
     lerr[1] = d1;
     kap[1] = k1 + d1;
     const float lstep = (d1 + g32 * k1) * 1.0001f;
-#pragma unroll
+    // rolled: one product body in the instruction stream (fully unrolled the kernel is 110 KB of straight-line code
+    // that every warp runs once - it then waits on instruction fetch); the three short arrays go to local memory
+#pragma unroll 1
     for (int j = 2; j <= B; j++) {
         if (j > 2) {
             square_step();
@@ -176,8 +179,7 @@ SDCGYM_HD void cert_envelope(const float (&Kr)[M * M], const float (&Ki)[M * M],
         khat[j] = wnorm(absX) * 1.0001f;
         lerr[j] = khat[j - 1] * lstep;
         float acc = khat[j];
-#pragma unroll
-        for (int i = 1; i <= j; i++) acc += lerr[i] * kap[j - i];
+        for (int i = 1; i <= j; i++) acc = fmaf(lerr[i], kap[j - i], acc);
         kap[j] = acc * 1.0001f;
     }
     // geometric envelope  ||K^n||_w <= G theta^n

@@ -123,6 +123,16 @@ SDCGYM_HD int sure_cmp(double lo, double up, double margin, double t) {
     return 0;
 }
 
+// second-stage decisions (rare): bits 0-1 = sure_cmp against thr + 1, bits 2-3 = sure_cmp against restol + 1
+template <int M>
+SDCGYM_HD_NOINLINE int stage2_decide(const double (&rr)[M], const double (&ri)[M], double margin, double thr, double restol) {
+    const double s2 = sq_absmax<M>(rr, ri);
+    if (!(s2 > 1e-280 && s2 < 1e300)) return 1 | (1 << 2);  // undecided
+    const double nr2 = dsqrt(s2);
+    const double lo = dmul(nr2, 1.0 - 2e-15), up = dmul(nr2, 1.0 + 2e-15);
+    return (sure_cmp(lo, up, margin, thr) + 1) | ((sure_cmp(lo, up, margin, restol) + 1) << 2);
+}
+
 // ---- the substitution step: one env per thread.  TRACE (host tests only): trace[k*(2M+2) ...] = r~_k (2M), ||r~_k||, margin_k ----
 template <int M, int V, bool TRACE = false>
 SDCGYM_HD void fast_step_one(const StepParams<M>& p, const FastWork& fw, const int64_t tid, double* trace = nullptr) {
@@ -205,15 +215,18 @@ SDCGYM_HD void fast_step_one(const StepParams<M>& p, const FastWork& fw, const i
             } else {
                 int ce = sure_cmp(lo, up, margin, thr), cc = sure_cmp(lo, up, margin, restol);
                 if (ce == 0 || (ce < 0 && cc == 0)) {
-                    // second stage: the norm itself (squared magnitudes: relative error < 1e-15)
-                    const double s2 = sq_absmax<M>(rr, ri);
-                    if (s2 > 1e-280 && s2 < 1e300) {
-                        const double nr2 = dsqrt(s2);
-                        lo = dmul(nr2, 1.0 - 2e-15);
-                        up = dmul(nr2, 1.0 + 2e-15);
-                        ce = sure_cmp(lo, up, margin, thr);
-                        cc = sure_cmp(lo, up, margin, restol);
+                    // second stage: the norm itself (squared magnitudes: relative error < 1e-15).  Out of line (and on a
+                    // private copy, so that rr / ri stay in registers): inlined, the compiler speculates its dozen
+                    // FP64 instructions into every sweep.
+                    double tr[M], ti[M];
+#pragma unroll
+                    for (int m = 0; m < M; m++) {
+                        tr[m] = rr[m];
+                        ti[m] = ri[m];
                     }
+                    const int both = stage2_decide<M>(tr, ti, margin, thr, restol);
+                    ce = (both & 3) - 1;
+                    cc = (both >> 2) - 1;
                 }
                 if (ce > 0) err = true;
                 else if (ce == 0) amb = true;
