@@ -275,6 +275,44 @@ def run_secondary(torch, np, dev, rank, world, barrier, max_over_ranks, fp64_pea
         "workload": "sdc-v0, Q_delta entries ~ U[0, 0.3] (do_scale=False), lambda ~ U[-100,0] + i U[-10,0]", "cases": sweep,
         "flops": "per sweep 8M^2+18M (lower_tri) / 8M^2+12M (strictly_lower_tri), set-up 15M + 2A (SURVEY 8d); the "
                  "bit-exact kernels execute more (the pivoted zgetf2 + ztrsm emulation of np.linalg.inv per step)"}
+    # ---- the certified substitution sweep mode (SDCGYM_SWEEP_CERTIFIED) against the exact mode on the headline workload
+    #      and on a workload where half of the envs converge (actions near the MIN preconditioner) ----
+    Nc = ENVS_PER_GPU
+    xmin = torch.as_tensor(np.ascontiguousarray(np.diag(fixed_preconditioner("min", 5))), device=dev)
+    modes = []
+    for wl in ("uniform", "near_MIN"):
+        if wl == "uniform":
+            acts = [torch.rand((Nc, 5), dtype=torch.float64, device=dev, generator=gen) * 2 - 1 for _ in range(2)]
+        else:
+            acts = [2 * (xmin[None] + (torch.rand((Nc, 5), dtype=torch.float64, device=dev, generator=gen) - 0.5) * 0.04) - 1
+                    for _ in range(2)]
+        res = {}
+        for mode in ("exact", "certified"):
+            env = sdc_gym_b200.make("sdc-v0", num_envs=Nc, M=5, env_offset=rank * Nc, sweep_mode=mode, **KW)
+            env.reset()
+            k = [0]
+
+            def f():
+                k[0] += 1
+                env.step_tensor(acts[k[0] % 2])
+
+            ms = timed(f, 4)
+            fb0 = env.fallback_stats()[1]
+            f()
+            fb = (env.fallback_stats()[1] - fb0) / Nc
+            res[mode] = dict(ms=ms, niter=env.info_niter[:Nc].clone(), flags=env.flags[:Nc].clone(), fb=fb)
+            del env
+        same = bool(torch.equal(res["exact"]["niter"], res["certified"]["niter"])
+                    and torch.equal(res["exact"]["flags"], res["certified"]["flags"]))
+        modes.append({"workload": wl, "exact_ms_per_step": res["exact"]["ms"], "certified_ms_per_step": res["certified"]["ms"],
+                      "certified_fallback_frac": res["certified"]["fb"], "niter_and_flags_bit_equal": same})
+        del acts, res
+        torch.cuda.empty_cache()
+    out["sweep_modes"] = {
+        "envs_per_gpu": Nc, "M": 5, "cases": modes,
+        "note": "certified = fp32 certificate kernel + substitution-sweep kernel + exact kernel over the fallback list "
+                "(csrc/certify.cuh, fast_kernels.cuh): same iteration counts and flags, u / r within rounding; the "
+                "headline `value` is measured in the exact mode"}
     # ---- config 4: spectral-radius loss on a 4096 x 4096 lambda grid, M = 5, MIN diagonal; rows sharded over the ranks ----
     G = args.grid
     loss = SpectralRadiusLoss(5, 1.0, "diag", device=dev)
@@ -417,7 +455,7 @@ def run_ours(args):
     for b in host_bufs:  # two action sets resident in page-locked host memory, used alternately
         b[:] = rng.uniform(-1, 1, (N, M))
 
-    def e2e_loop(e, steps, copy_outputs=False):
+    def e2e_loop(e, steps, copy_outputs=False, read_infos=False):
         checksum = 0.0
         for k in range(min(3, args.warmup)):
             e.step(host_bufs[k % 2])
@@ -428,7 +466,9 @@ def run_ours(args):
             if copy_outputs:  # what a caller pays who must own fresh, contiguous arrays every step
                 obs, rew, done = np.array(obs, order="C"), rew.copy(), done.copy()
                 keep = (infos.niter.copy(), infos.residual.copy(), infos.lam.copy())  # noqa: F841
-            checksum += float(rew[0]) + float(obs[0, 1, 0].real)
+            if read_infos:  # a caller that looks at info['niter' / 'residual' / 'lam'] after every step
+                checksum += float(infos.niter[0]) + float(infos.residual[0]) + float(infos.lam[0].real)
+            checksum += float(rew[0]) + float(obs[0, 1, 0].real) + float(done[0])
         barrier()
         return max_over_ranks(time.perf_counter() - t0), checksum
 
@@ -436,9 +476,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * N * args.steps / e2e_s
     h2d = N * M * 8
-    d2h = N * (M * 16 + 8 + 1 + 4 + 8 + 16)  # residual row (the u row of sdc-v0's reset state is constant), reward,
-    #                                           flags, niter, residual norm, lambda
+    lazy = bool(getattr(env, "lazy_info", False)) and N >= 32768
+    d2h_info = N * (4 + 8 + 16)  # niter, residual norm, lambda: fetched when an info dict / array is read (lazy_info)
+    d2h = N * (M * 16 + 8 + 1) + (0 if lazy else d2h_info)  # residual row (the u row of sdc-v0's reset state is
+    #                                                          constant), reward, flags [+ info arrays]
     host_sets, host_copies = len(env._host["sets"]), env.host_set_copies
+    infos_s, _ = e2e_loop(env, args.steps, read_infos=True)
     env.reuse_buffers = True
     reuse_s, _ = e2e_loop(env, args.steps)
     copy_s, _ = e2e_loop(env, max(2, args.steps // 2), copy_outputs=True)
@@ -452,11 +495,16 @@ def run_ours(args):
     a_dev, a_host = env.action_dev, env._host["actions"][0]
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
+    lay = env._layout
+    segs = [(int(lay.reward), int(lay.residual)), (int(lay.flags), int(lay.total))] if lazy else [(skip, int(lay.total))]
+    moved = sum(b - a for a, b in segs)
+
     def copies():
         with torch.cuda.stream(s1):
             a_dev.copy_(a_host, non_blocking=True)
         with torch.cuda.stream(s2):
-            hb[skip:].copy_(dsrc[skip:], non_blocking=True)
+            for a, b in segs:
+                hb[a:b].copy_(dsrc[a:b], non_blocking=True)
 
     for _ in range(3):
         copies()
@@ -470,9 +518,9 @@ def run_ours(args):
     pcie_s = max_over_ranks(time.perf_counter() - t0)
     pcie_value = world * N * args.steps / pcie_s
     pcie = {"value": pcie_value, "unit": UNIT, "ms_per_step": 1e3 * pcie_s / args.steps,
-            "d2h_GBps_per_gpu": (int(env._layout.total) - skip) / (pcie_s / args.steps) / 1e9,
+            "d2h_GBps_per_gpu": moved / (pcie_s / args.steps) / 1e9,
             "how": f"{world} rank(s) concurrently: cudaMemcpyAsync of one step's bytes (H2D {h2d} B on one stream, D2H "
-                   f"{int(env._layout.total) - skip} B on another, page-locked host memory), no kernels",
+                   f"{moved} B on another, page-locked host memory), no kernels",
             "e2e_frac": e2e_value / pcie_value}
 
     # ---------------- secondary: BASELINE configs 3, 4, 5 (bounded) ----------------
@@ -522,7 +570,13 @@ def run_ours(args):
                            "once the caller has dropped them (terminal observations stay on the device until an info "
                            "dict asks for them; the u row of sdc-v0's returned reset state is constant and not moved)",
                     "host_result_blocks": host_sets, "steps_that_copied": host_copies,
-                    "variants": {"reuse_buffers": {"value": world * N * args.steps / reuse_s, "unit": UNIT,
+                    "info_arrays": ("niter / residual / lam (28 B per env) stay in the device block until an info dict or "
+                                    "array is read (lazy_info, batches >= 32768 envs); variants.reading_infos_every_step "
+                                    "pays for them") if lazy else "transferred with every step",
+                    "variants": {"reading_infos_every_step": {"value": world * N * args.steps / infos_s, "unit": UNIT,
+                                                              "ms_per_step": 1e3 * infos_s / args.steps,
+                                                              "d2h_bytes_per_step": d2h + (d2h_info if lazy else 0)},
+                                 "reuse_buffers": {"value": world * N * args.steps / reuse_s, "unit": UNIT,
                                                    "ms_per_step": 1e3 * reuse_s / args.steps},
                                  "fresh_copy_of_every_output": {"value": world * N * copy_steps / copy_s, "unit": UNIT,
                                                                 "ms_per_step": 1e3 * copy_s / copy_steps}},

@@ -338,7 +338,10 @@ typedef struct sdcgym_block_io {
     double* action_dev;        /* device staging [N][A] ([N][A][2] complex) */
     const double* action_host; /* host actions, same shape (page-locked for asynchronous upload) */
     double* terminal_obs;      /* device planes [4M][ld] or NULL (terminal observations not kept) */
-    int32_t skip_u;            /* 1: u rows are constant, neither exported nor transferred */
+    int32_t skip_u;            /* bit 0: u rows are constant, neither exported nor transferred;
+                                * bit 1: info arrays (niter, residual, lam: 28 of 117 bytes per env) stay in the device
+                                *        block when the batch is large enough to be pipelined in chunks - the caller
+                                *        copies [layout.residual, layout.flags) on demand (info dicts are read lazily) */
     int32_t chunks;            /* <= 0: chosen by the library from the batch size */
 } sdcgym_block_io;
 /* env.step with host actions in, host results out (see sdcgym_pipe_step); returns when the host block is filled.

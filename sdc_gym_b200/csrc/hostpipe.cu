@@ -465,7 +465,8 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
     cudaStream_t cs = (cudaStream_t)caller_stream;
     unsigned char* db = bio->dev_block;
     unsigned char* hb = bio->host_block;
-    const bool skip_u = bio->skip_u != 0 && !(vn && vn->norm_obs);  // normalised u rows are not constant
+    const bool skip_u = (bio->skip_u & 1) != 0 && !(vn && vn->norm_obs);  // normalised u rows are not constant
+    const bool lazy_info = (bio->skip_u & 2) != 0;  // chunked path only: niter / residual / lam stay in the device block
     const int P2 = 2 * M;                                            // planes per observation row (u or r)
     const size_t row_bytes = (size_t)P2 * sizeof(double);
 
@@ -576,9 +577,11 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
             const int64_t sn = hi - small_lo;
             SEG(p->s_out2, L->reward, small_lo, sn, sizeof(double))
             SEG(p->s_out2, L->flags, small_lo, sn, 1)
-            SEG(p->s_out2, L->niter, small_lo, sn, sizeof(int32_t))
-            SEG(p->s_out2, L->residual, small_lo, sn, sizeof(double))
-            SEG(p->s_out2, L->lam, small_lo, sn, 2 * sizeof(double))
+            if (!lazy_info) {
+                SEG(p->s_out2, L->niter, small_lo, sn, sizeof(int32_t))
+                SEG(p->s_out2, L->residual, small_lo, sn, sizeof(double))
+                SEG(p->s_out2, L->lam, small_lo, sn, 2 * sizeof(double))
+            }
             small_lo = hi;
             if (trace) {
                 cudaEventRecord(g_trace.small[c], p->s_out2);

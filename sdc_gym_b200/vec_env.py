@@ -18,6 +18,7 @@ from __future__ import annotations
 import ctypes
 import os
 import sys
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -60,14 +61,37 @@ class LazyInfos(Sequence):
     ``TimeLimit.truncated`` appear for finished envs exactly as DummyVecEnv / TimeLimit add them.
     """
 
-    def __init__(self, niter, residual, lam, done, truncated_key, terminal_fetch):
-        self.niter, self.residual, self.lam, self.done = niter, residual, lam, done
+    def __init__(self, niter, residual, lam, done, truncated_key, terminal_fetch, info_fetch=None):
+        self._niter, self._residual, self._lam, self.done = niter, residual, lam, done
         self._truncated_key = truncated_key
         self._terminal_fetch = terminal_fetch
         self._terminal = None
+        # large pipelined batches leave niter / residual / lam (28 of 117 bytes per env) on the device until somebody
+        # reads them: `info_fetch` copies them into the (already allocated) arrays above
+        self._info_fetch = info_fetch
+
+    def _info(self):
+        if self._info_fetch is not None:
+            fetch, self._info_fetch = self._info_fetch, None
+            fetch()
+
+    @property
+    def niter(self):
+        self._info()
+        return self._niter
+
+    @property
+    def residual(self):
+        self._info()
+        return self._residual
+
+    @property
+    def lam(self):
+        self._info()
+        return self._lam
 
     def __len__(self):
-        return len(self.niter)
+        return len(self.done)
 
     def terminal_observations(self):
         if self._terminal is None:
@@ -135,10 +159,11 @@ class _TruncatedKey:
     ``max_episode_steps`` steps (always for sdc-v0, at niter >= 50 for sdc-v1).  Evaluated lazily."""
 
     def __init__(self, niter, max_steps):
-        self._niter, self._max = niter, max_steps
+        self._niter, self._max = niter, max_steps  # `niter`: an array, or a callable returning it (lazy info arrays)
 
     def __getitem__(self, i):
-        return bool(self._niter[i] >= self._max)
+        n = self._niter() if callable(self._niter) else self._niter
+        return bool(n[i] >= self._max)
 
 
 class _EnvProxy:
@@ -235,6 +260,7 @@ class SDCVecEnv:
         max_host_sets: int = 4,
         keep_terminal: bool = True,
         sweep_mode: str = "exact",
+        lazy_info: bool = True,
     ):
         torch = _torch()
         if envname not in _lib.ENV_KINDS:
@@ -341,6 +367,7 @@ class SDCVecEnv:
         self.host_pipeline = host_pipeline
         self.max_host_sets = max(1, int(max_host_sets))
         self.keep_terminal = bool(keep_terminal)
+        self.lazy_info = bool(lazy_info)
         self._pipe = None
         self._bio = None
         self._step_count = 0
@@ -740,7 +767,7 @@ class SDCVecEnv:
             bio.dev_block = self.dev_block.data_ptr()
             bio.action_dev = self.action_dev.data_ptr() if self._kernel_n_act else None
             bio.terminal_obs = self.terminal.data_ptr() if self.terminal is not None else None
-            bio.skip_u = int(self._const_u)
+            bio.skip_u = int(self._const_u) | (2 if self.lazy_info else 0)
             self._bio = (bio, self._state())
         self._bio[0].chunks = self.pipeline_chunks
         return self._bio
@@ -761,7 +788,9 @@ class SDCVecEnv:
                    "sdcgym_pipe_step_block")
         self._step_count += 1
         self._invalidate()
-        return self._host_outputs(hs, owned)
+        lazy = (self.lazy_info and vn is None
+                and (self.pipeline_chunks > 1 or (self.pipeline_chunks <= 0 and self.num_envs >= 32768)))
+        return self._host_outputs(hs, owned, lazy)
 
     def _step_simple(self, actions):
         """Unpipelined host step (rarely used configurations): upload, device step, download."""
@@ -781,12 +810,15 @@ class SDCVecEnv:
         infos.flags = flags
         return obs, out["reward"].cpu().numpy(), dones, infos
 
-    def _host_outputs(self, hs, owned):
+    def _host_outputs(self, hs, owned, lazy_info=False):
         if owned:
             cp = lambda x: x  # noqa: E731 - the block is the caller's until they drop it (see _acquire_set)
         else:
             self.host_set_copies += 1
             cp = np.ascontiguousarray if hs.obs.flags.c_contiguous else (lambda x: np.array(x, order="C"))
+        if lazy_info and not owned:  # the copies below must see the info arrays
+            self._fetch_info_into(hs)
+            lazy_info = False
         obs, rewards, flags = cp(hs.obs), cp(hs.reward), cp(hs.flags)
         if owned:  # no per-step allocation: the mask lands in the block's own `dones` array
             np.bitwise_and(flags, _lib.FLAG_DONE, out=hs._done_u8)
@@ -794,10 +826,32 @@ class SDCVecEnv:
         else:
             dones = np.bitwise_and(flags, _lib.FLAG_DONE).view(np.bool_)
         niter = cp(hs.niter)
-        infos = LazyInfos(niter, cp(hs.residual), cp(hs.lam), dones, _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname]),
-                          self._terminal_fetcher())
+        fetch = None
+        if lazy_info:
+            stamp = self._step_count
+
+            def fetch():
+                if self._step_count != stamp:
+                    raise RuntimeError("info['niter' / 'residual' / 'lam'] of this step are gone: the env has stepped "
+                                       "since (large batches keep them on the device until they are read; read them "
+                                       "before the next step or construct the env with lazy_info=False)")
+                self._fetch_info_into(hs)
+
+        infos = LazyInfos(niter, cp(hs.residual), cp(hs.lam), dones, None, self._terminal_fetcher(), fetch)
+        if lazy_info:  # (weak reference: a cycle would keep the result block referenced until the next gc run)
+            ref = weakref.ref(infos)
+            infos._truncated_key = _TruncatedKey(lambda: ref().niter, MAX_EPISODE_STEPS[self.envname])
+        else:
+            infos._truncated_key = _TruncatedKey(niter, MAX_EPISODE_STEPS[self.envname])
         infos.flags = flags
         return obs, rewards, dones, infos
+
+    def _fetch_info_into(self, hs):
+        """niter / residual / lam of the last step: device block -> the same bytes of the host block ``hs``."""
+        lay = self._layout
+        lo, hi = int(lay.residual), int(lay.flags)  # residual, lam, niter are adjacent (sdcgym_block_layout_init)
+        with self._guard:
+            hs.blk[lo:hi].copy_(self.dev_block[lo:hi])
 
     def _terminal_fetcher(self):
         """``info['terminal_observation']`` is served lazily from the device's terminal planes, which the NEXT step

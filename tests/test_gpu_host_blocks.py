@@ -237,3 +237,40 @@ def test_gym_adapter_single_env_matches_oracle():
             break
     assert env.M == 5 and env.restol == 1e-10 and env.prec is None
     assert isinstance(sdc_gym_b200.register_gym(), list)
+
+
+def test_lazy_info_arrays_of_large_batches():
+    """Batches that are pipelined in chunks leave niter / residual / lam on the device until they are read
+    (lazy_info, default): same values as the eager path, fetched once, refused after the env has stepped again."""
+    import sdc_gym_b200
+
+    N, M = 40000, 5  # >= 32768: chunked pipeline
+    kw = dict(num_envs=N, M=M, dt=1.0, restol=1e-10, seed=5, lambda_real_interval=[-100, 0],
+              lambda_imag_interval=[-10, 0])
+    lazy = sdc_gym_b200.make("sdc-v0", **kw)
+    eager = sdc_gym_b200.make("sdc-v0", lazy_info=False, **kw)
+    lazy.reset()
+    eager.reset()
+    act = np.random.default_rng(0).uniform(-1, 1, (N, M))
+    o1, r1, d1, i1 = lazy.step(act)
+    o2, r2, d2, i2 = eager.step(act)
+    assert i1._info_fetch is not None and i2._info_fetch is None
+    assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    assert np.array_equal(i1.niter, i2.niter) and i1._info_fetch is None  # fetched by the first access
+    assert np.array_equal(i1.residual, i2.residual) and np.array_equal(i1.lam, i2.lam)
+    d = i1[7]
+    assert d["niter"] == int(i2.niter[7]) and d["lam"] == complex(i2.lam[7]) and "TimeLimit.truncated" in d
+    # per-env dict access alone triggers the fetch as well
+    o1, r1, d1, i1 = lazy.step(act)
+    o2, r2, d2, i2 = eager.step(act)
+    assert i1[3]["residual"] == i2[3]["residual"]
+    # not read before the next step: gone, and said so
+    _, _, _, stale = lazy.step(act)
+    lazy.step(act)
+    with pytest.raises(RuntimeError):
+        stale.niter
+    # small batches always carry their info arrays
+    small = sdc_gym_b200.make("sdc-v0", **{**kw, "num_envs": 64})
+    small.reset()
+    _, _, _, inf = small.step(act[:64])
+    assert inf._info_fetch is None and inf.niter.shape == (64,)
