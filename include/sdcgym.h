@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 5 /* 5: sweep_mode (certified substitution sweeps) + its work buffers in sdcgym_state */
+#define SDCGYM_ABI_VERSION 6 /* 5: sweep_mode + work buffers in sdcgym_state; 6: in-kernel peer-memory statistics exchange */
 #define SDCGYM_MAX_M 9
 #define SDCGYM_CERT_PLANES 8
 
@@ -246,6 +246,35 @@ int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double*
                           double* scratch, double* sums, void* stream);
 int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, double gamma, double* returns, double* mean,
                                   double* var, double* count2, double* scratch, double* sums, void* stream);
+/*
+ * Several ranks (one process per GPU, envs sharded): the same single launch, with the all-reduce of the
+ * moment sums done INSIDE the kernel over peer memory (NVLink / NVSwitch P2P stores and flags) instead of
+ * accumulate -> ncclAllReduce -> merge.  Every rank owns an exchange region of sdcgym_xchg_bytes(world, slot_doubles)
+ * bytes (slot_doubles >= 2P + 1), allocated with sdcgym_ipc_alloc and opened by the other ranks' processes with
+ * sdcgym_ipc_open (the 64-byte handles travel over the host-side process group); `peers[r]` is rank r's region as
+ * seen from this process (`peers[rank]` the local one).  `seq` must be 1, 2, 3, ... for successive calls on one set of
+ * regions, identically on all ranks; all ranks must make the call (a rank with N = 0 included).  The sums are added
+ * in rank order on every rank, so the normalisers stay bit-identical across ranks.
+ */
+#define SDCGYM_MAX_RANKS 16
+typedef struct sdcgym_xchg {
+    int32_t world, rank;
+    int32_t slot_doubles, reserved;
+    uint64_t seq;
+    void* peers[SDCGYM_MAX_RANKS];
+} sdcgym_xchg;
+size_t sdcgym_xchg_bytes(int world, int slot_doubles);
+int sdcgym_vecnorm_update_dist(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var, double* count2,
+                               double* scratch, double* sums, const sdcgym_xchg* xchg, void* stream);
+int sdcgym_vecnorm_update_returns_dist(int64_t N, const double* reward, double gamma, double* returns, double* mean,
+                                       double* var, double* count2, double* scratch, double* sums,
+                                       const sdcgym_xchg* xchg, void* stream);
+/* device memory that other processes can map: cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle
+ * (with peer access enabled lazily) / close / free */
+int sdcgym_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int sdcgym_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int sdcgym_ipc_close(void* dev_ptr);
+int sdcgym_ipc_free(void* dev_ptr);
 int sdcgym_vecnorm_apply(int P, int64_t N, int64_t ld, const double* X, const double* mean, const double* var, double eps,
                          double clip, double* Y, void* stream);
 int sdcgym_vecnorm_returns(int64_t N, const double* reward, double gamma, double* returns, void* stream);

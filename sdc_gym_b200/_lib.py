@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
 
 MAX_M = 9
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -216,6 +216,16 @@ class VecNorm(ctypes.Structure):
     ]
 
 
+MAX_RANKS = 16
+
+
+class Xchg(ctypes.Structure):
+    """struct sdcgym_xchg"""
+
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("slot_doubles", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("seq", ctypes.c_uint64), ("peers", ctypes.c_void_p * MAX_RANKS)]
+
+
 class SdcGymError(RuntimeError):
     pass
 
@@ -263,6 +273,17 @@ def load():
     L.sdcgym_vecnorm_update.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_update_returns.argtypes = [i64, vp, dbl, vp, vp, vp, vp, vp, vp, vp]
     L.sdcgym_vecnorm_apply.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, dbl, dbl, vp, vp]
+    L.sdcgym_xchg_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.sdcgym_xchg_bytes.restype = ctypes.c_size_t
+    L.sdcgym_vecnorm_update_dist.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(Xchg), vp]
+    L.sdcgym_vecnorm_update_returns_dist.argtypes = [i64, vp, dbl, vp, vp, vp, vp, vp, vp, ctypes.POINTER(Xchg), vp]
+    L.sdcgym_ipc_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.sdcgym_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.sdcgym_ipc_close.argtypes = [vp]
+    L.sdcgym_ipc_free.argtypes = [vp]
+    for name in ("sdcgym_vecnorm_update_dist", "sdcgym_vecnorm_update_returns_dist", "sdcgym_ipc_alloc",
+                 "sdcgym_ipc_open", "sdcgym_ipc_close", "sdcgym_ipc_free"):
+        getattr(L, name).restype = ctypes.c_int
     L.sdcgym_vecnorm_returns.argtypes = [i64, vp, dbl, vp, vp]
     L.sdcgym_vecnorm_reward.argtypes = [i64, vp, vp, vp, dbl, dbl, ctypes.c_int, vp, vp, vp]
     L.sdcgym_pipe_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
@@ -311,4 +332,4 @@ def exported_symbols():
     header = os.path.join(os.path.dirname(_HERE), "include", "sdcgym.h")
     with open(header) as f:
         text = f.read()
-    return sorted(set(re.findall(r"\bint\s+(sdcgym_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(?:int|size_t)\s+(sdcgym_[a-z0-9_]+)\s*\(", text)))

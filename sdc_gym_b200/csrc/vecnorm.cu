@@ -8,6 +8,7 @@
 //
 // All reductions use a fixed block count and a fixed summation tree: deterministic run to run.
 #include <cuda_runtime.h>
+#include <string.h>
 #include <math_constants.h>
 
 #include "../../include/sdcgym.h"
@@ -120,12 +121,35 @@ __global__ void rms_commit_kernel(double* __restrict__ count) { count[0] = count
 // sequence accumulate -> merge -> commit, without the three launches (a normalised sdc-v1 step of 2^20 envs is a
 // 115 us kernel: five 2-7 us launches per statistic were a fifth of the step).
 // RETURNS: the plane is the discounted return, advanced in the same pass: ret <- ret * gamma + reward.
-template <bool RETURNS>
+//
+// Several ranks (one process per GPU): the same launch also performs the all-reduce of the moment sums, over peer
+// memory (NVLink / NVSwitch P2P stores into every rank's exchange region, include/sdcgym.h sdcgym_xchg) instead of an
+// NCCL call between an accumulate and a merge kernel: the block that folds this rank's partial sums
+//   1. stores its 2P + 1 numbers (shifted sums, shifted square sums, env count) into slot [parity][rank] of EVERY rank's
+//      region, fences system-wide and raises flag [parity][rank] = seq there,
+//   2. waits until the `world` flags of its own region show seq,
+//   3. adds the slots in rank order (the same order on every rank: the normalisers stay bit-identical) and merges.
+// Two parities: a rank can be at most one exchange ahead of a peer (it needs the peer's flag of the previous one).
+struct XchgDev {
+    int world, rank;
+    unsigned long long seq;
+    int stride;  // doubles per slot
+    double* peer[SDCGYM_MAX_RANKS];  // exchange regions of all ranks (peer[rank] = the local one)
+};
+__device__ __forceinline__ double* xchg_slot(double* region, int world, int stride, int parity, int r) {
+    return region + ((size_t)parity * world + r) * stride;
+}
+__device__ __forceinline__ unsigned long long* xchg_flags(double* region, int world, int stride, int parity) {
+    return reinterpret_cast<unsigned long long*>(region + (size_t)2 * world * stride) + (size_t)parity * world;
+}
+
+template <bool RETURNS, bool DIST>
 __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
                                                              const double* __restrict__ reward, double gamma,
                                                              double* __restrict__ ret, double* mean, double* var,
                                                              double* count, double* __restrict__ partial,
-                                                             double* __restrict__ sums, unsigned int* ticket) {
+                                                             double* __restrict__ sums, unsigned int* ticket,
+                                                             const XchgDev xc) {
     const int p = blockIdx.y;
     const double s = mean[p];
     double a = 0.0, b = 0.0;
@@ -159,20 +183,71 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const double n = count[0], batch = (double)N;
+    const double n = count[0];
+    double batch = (double)N;
     __syncthreads();
-    for (int q = threadIdx.x; q < P; q += kAccThreads) {
-        double sa = 0.0, sb = 0.0;
-        for (int k = 0; k < kAccBlocks; k++) {
-            sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
-            sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+    if (DIST) {
+        // ---- fold the local partials, publish them to every rank, wait for everybody's ----
+        const int parity = (int)(xc.seq & 1ull);
+        for (int q = threadIdx.x; q < P; q += kAccThreads) {
+            double sa = 0.0, sb = 0.0;
+            for (int k = 0; k < kAccBlocks; k++) {
+                sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
+                sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+            }
+            for (int r = 0; r < xc.world; r++) {
+                double* slot = xchg_slot(xc.peer[r], xc.world, xc.stride, parity, xc.rank);
+                slot[q] = sa;
+                slot[P + q] = sb;
+            }
         }
-        sums[q] = sa;
-        sums[P + q] = sb;
-        double m = mean[q], v = var[q];
-        rms_merge_one(n, batch, sa, sb, m, v);
-        mean[q] = m;
-        var[q] = v;
+        if (threadIdx.x == 0)
+            for (int r = 0; r < xc.world; r++) xchg_slot(xc.peer[r], xc.world, xc.stride, parity, xc.rank)[2 * P] = batch;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < xc.world) {
+            volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
+            *remote = xc.seq;
+        }
+        if (threadIdx.x < xc.world) {
+            volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
+            while (*mine != xc.seq) {
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        double* region = xc.peer[xc.rank];
+        batch = 0.0;
+        for (int r = 0; r < xc.world; r++)
+            batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, r) + 2 * P);
+        for (int q = threadIdx.x; q < P; q += kAccThreads) {
+            double sa = 0.0, sb = 0.0;
+            for (int r = 0; r < xc.world; r++) {
+                const double* slot = xchg_slot(region, xc.world, xc.stride, parity, r);
+                sa += __ldcv(slot + q);
+                sb += __ldcv(slot + P + q);
+            }
+            sums[q] = sa;
+            sums[P + q] = sb;
+            double m = mean[q], v = var[q];
+            if (batch > 0.0) rms_merge_one(n, batch, sa, sb, m, v);
+            mean[q] = m;
+            var[q] = v;
+        }
+    } else {
+        for (int q = threadIdx.x; q < P; q += kAccThreads) {
+            double sa = 0.0, sb = 0.0;
+            for (int k = 0; k < kAccBlocks; k++) {
+                sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
+                sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+            }
+            sums[q] = sa;
+            sums[P + q] = sb;
+            double m = mean[q], v = var[q];
+            rms_merge_one(n, batch, sa, sb, m, v);
+            mean[q] = m;
+            var[q] = v;
+        }
     }
     if (threadIdx.x == 0) {
         count[0] = n + batch;
@@ -180,6 +255,7 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
         *ticket = 0u;  // self-cleaning: ready for the next launch on this stream
     }
 }
+
 
 __global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X, const double* __restrict__ mean,
                              const double* __restrict__ var, double eps, double clip, double* __restrict__ Y) {
@@ -399,8 +475,8 @@ extern "C" int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double*
     if (N == 0) return 0;
     if (!X || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)P * kAccBlocks * 2);
-    update_kernel<false><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
-        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket);
+    update_kernel<false, false><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
+        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket, XchgDev{});
     return (int)cudaGetLastError();
 }
 
@@ -410,10 +486,90 @@ extern "C" int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, do
     if (N == 0) return 0;
     if (!reward || !returns || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
-    update_kernel<true><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
-        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket);
+    update_kernel<true, false><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
+        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket, XchgDev{});
     return (int)cudaGetLastError();
 }
+
+// ---- multi-rank: the same single launch with the all-reduce of the moment sums over peer memory ------------------
+static int fill_xchg(const sdcgym_xchg* x, int P, XchgDev& d) {
+    if (!x) return SDCGYM_ENULL;
+    if (x->world < 1 || x->world > SDCGYM_MAX_RANKS || x->rank < 0 || x->rank >= x->world) return SDCGYM_EINVAL;
+    if (x->slot_doubles < 2 * P + 1 || x->seq == 0) return SDCGYM_EINVAL;
+    d.world = x->world;
+    d.rank = x->rank;
+    d.seq = x->seq;
+    d.stride = x->slot_doubles;
+    for (int r = 0; r < x->world; r++) {
+        if (!x->peers[r]) return SDCGYM_ENULL;
+        d.peer[r] = static_cast<double*>(x->peers[r]);
+    }
+    return 0;
+}
+
+extern "C" size_t sdcgym_xchg_bytes(int world, int slot_doubles) {
+    if (world < 1 || slot_doubles < 1) return 0;
+    return ((size_t)2 * world * slot_doubles) * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+}
+
+extern "C" int sdcgym_vecnorm_update_dist(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
+                                          double* count2, double* scratch, double* sums, const sdcgym_xchg* xchg,
+                                          void* stream) {
+    if (P < 1 || P > kAccThreads * 4 || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if ((N > 0 && !X) || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
+    XchgDev d{};
+    int rc = fill_xchg(xchg, P, d);
+    if (rc) return rc;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)P * kAccBlocks * 2);
+    // (an empty shard still takes part in the exchange)
+    update_kernel<false, true><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
+        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket, d);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_update_returns_dist(int64_t N, const double* reward, double gamma, double* returns,
+                                                  double* mean, double* var, double* count2, double* scratch,
+                                                  double* sums, const sdcgym_xchg* xchg, void* stream) {
+    if (N < 0) return SDCGYM_EINVAL;
+    if ((N > 0 && (!reward || !returns)) || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
+    XchgDev d{};
+    int rc = fill_xchg(xchg, 1, d);
+    if (rc) return rc;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
+    update_kernel<true, true><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
+        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket, d);
+    return (int)cudaGetLastError();
+}
+
+// ---- exchange regions: cudaMalloc'd (legacy CUDA IPC needs that), zeroed, shared between the ranks' processes by IPC
+//      handle; opening a handle enables peer access to the owning device ----
+extern "C" int sdcgym_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+    if (!dev_ptr || !handle64) return SDCGYM_ENULL;
+    if (bytes == 0) return SDCGYM_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return (int)e;
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return 0;
+}
+extern "C" int sdcgym_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return SDCGYM_ENULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return (int)cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+extern "C" int sdcgym_ipc_close(void* dev_ptr) { return dev_ptr ? (int)cudaIpcCloseMemHandle(dev_ptr) : 0; }
+extern "C" int sdcgym_ipc_free(void* dev_ptr) { return dev_ptr ? (int)cudaFree(dev_ptr) : 0; }
 
 extern "C" int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift,
                                          double* scratch, double* sums, void* stream) {

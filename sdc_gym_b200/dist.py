@@ -57,6 +57,63 @@ def all_reduce_sum(t):
     return t
 
 
+class PeerExchange:
+    """Exchange regions for the in-kernel all-reduce of the normaliser moments (include/sdcgym.h ``sdcgym_xchg``):
+    every rank allocates one region, the 64-byte CUDA IPC handles travel over the process group (the only use of the
+    host-side collective: once, at set-up), every rank maps all the others' regions.  ``struct(seq)`` fills the
+    argument block of ``sdcgym_vecnorm_update*_dist``."""
+
+    def __init__(self, slot_doubles: int):
+        import ctypes
+
+        from . import _lib
+
+        L = _lib.load()
+        dist = _dist()
+        self._L = L
+        self.rank, self.world = world()
+        if self.world > _lib.MAX_RANKS:
+            raise _lib.SdcGymError(f"peer exchange supports up to {_lib.MAX_RANKS} ranks")
+        self.slot = int(slot_doubles)
+        nbytes = L.sdcgym_xchg_bytes(self.world, self.slot)
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(L.sdcgym_ipc_alloc(nbytes, ctypes.byref(ptr), handle), "sdcgym_ipc_alloc")
+        self._own = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self.peers = [None] * self.world
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peers[r] = self._own
+                continue
+            q = ctypes.c_void_p()
+            _lib.check(L.sdcgym_ipc_open(h, ctypes.byref(q)), f"sdcgym_ipc_open (rank {r})")
+            self.peers[r] = q.value
+            self._opened.append(q.value)
+        dist.barrier()  # nobody launches an exchange before every region is mapped everywhere
+        self.seq = 0
+        self._struct = _lib.Xchg()
+        self._struct.world, self._struct.rank, self._struct.slot_doubles = self.world, self.rank, self.slot
+        for r, q in enumerate(self.peers):
+            self._struct.peers[r] = q
+
+    def next(self):
+        """The argument struct for the next exchange (sequence numbers 1, 2, 3, ... in lock step on all ranks)."""
+        self.seq += 1
+        self._struct.seq = self.seq
+        return self._struct
+
+    def close(self):
+        for q in self._opened:
+            self._L.sdcgym_ipc_close(q)
+        self._opened = []
+        if self._own:
+            self._L.sdcgym_ipc_free(self._own)
+            self._own = None
+
+
 def chan_merge(mean, var, count, shifted_sum, shifted_sumsq, batch_count):
     """Host restatement of ``rms_merge_kernel`` (SB3 ``RunningMeanStd.update_from_moments``): the batch is described
     by sums of (x - mean) and (x - mean)^2 over ``batch_count`` samples.  Works on numpy arrays or tensors."""

@@ -94,6 +94,10 @@ class VecNormalize:
         self._scratch = torch.zeros(nscr, dtype=torch.float64, device=dev)
         self._rscratch = torch.zeros(self._L.sdcgym_vecnorm_scratch_doubles(1), dtype=torch.float64, device=dev)
         self.fused_update = True  # single-rank: accumulate + merge in one launch (False: the three-kernel sequence)
+        # several ranks: sync=True / "peer" folds the all-reduce of the moment sums into the statistics kernel (P2P
+        # stores into every rank's exchange region over NVLink, csrc/vecnorm.cu update_kernel<.., DIST>);
+        # sync="nccl" keeps accumulate -> ncclAllReduce -> merge
+        self._xchg_obs = self._xchg_ret = None
         # shifted sums of the observation planes and of the returns, contiguous so that a multi-rank step needs ONE
         # all-reduce for both statistics
         self._allsums = torch.zeros(2 * self.P + 1 + 3, dtype=torch.float64, device=dev)
@@ -123,8 +127,24 @@ class VecNormalize:
     def _multi_rank(self):
         return self.sync and _dist_mod.is_distributed()
 
+    def _peer_mode(self):
+        """True when the multi-rank statistics go through the in-kernel peer-memory exchange."""
+        if not self._multi_rank() or self.sync == "nccl" or not self.fused_update:
+            return False
+        if self._xchg_obs is None:
+            self._xchg_obs = _dist_mod.PeerExchange(2 * self.P + 1)
+            self._xchg_ret = _dist_mod.PeerExchange(3)
+        return True
+
     def _update(self, rms, planes_ptr, P, N, ld, sums):
         L, s = self._L, self._stream()
+        if self._peer_mode():
+            x = self._xchg_obs if P > 1 else self._xchg_ret
+            scratch = self._scratch if P > 1 else self._rscratch
+            _lib.check(L.sdcgym_vecnorm_update_dist(P, N, ld, planes_ptr, rms.mean.data_ptr(), rms.var.data_ptr(),
+                                                    rms.count2.data_ptr(), scratch.data_ptr(), sums.data_ptr(),
+                                                    ctypes.byref(x.next()), s), "vecnorm_update_dist")
+            return
         if self.fused_update and not self._multi_rank():
             scratch = self._scratch if P > 1 else self._rscratch
             _lib.check(L.sdcgym_vecnorm_update(P, N, ld, planes_ptr, rms.mean.data_ptr(), rms.var.data_ptr(),
@@ -190,7 +210,8 @@ class VecNormalize:
         N = v.num_envs
         # several ranks, both statistics live: accumulate both, ONE all-reduce (the only collective of a normalised
         # step), merge both - instead of one collective per statistic
-        combined = self.training and self.norm_obs and self._multi_rank()
+        peer = self.training and self._peer_mode()
+        combined = self.training and self.norm_obs and self._multi_rank() and not peer
         if combined:
             self._accumulate(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
             _lib.check(L.sdcgym_vecnorm_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(), s), "returns")
@@ -219,6 +240,13 @@ class VecNormalize:
         out["raw_reward"] = raw["reward"]
         if combined:
             pass  # return statistics already updated above
+        elif peer:
+            r = self.ret_rms
+            _lib.check(L.sdcgym_vecnorm_update_returns_dist(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(),
+                                                            r.mean.data_ptr(), r.var.data_ptr(), r.count2.data_ptr(),
+                                                            self._rscratch.data_ptr(), self._rsums.data_ptr(),
+                                                            ctypes.byref(self._xchg_ret.next()), s),
+                       "vecnorm_update_returns_dist")
         elif self.training and self.fused_update and not self._multi_rank():
             r = self.ret_rms
             _lib.check(L.sdcgym_vecnorm_update_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(),

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--rollouts", type=int, default=5)
+ap.add_argument("--sync", default="peer", choices=["peer", "nccl"], help="peer: all-reduce of the moment sums inside the statistics kernel over NVLink peer memory; nccl: accumulate -> ncclAllReduce -> merge")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -26,7 +27,7 @@ N, T, M = args.envs_per_gpu, args.steps, 5
 env = sdc_gym_b200.VecNormalize(
     sdc_gym_b200.make("sdc-v1", num_envs=N, M=M, dt=1.0, restol=1e-10, seed=0, env_offset=rank * N,
                       reward_iteration_only=False, lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0],
-                      device=dev), norm_obs=True, norm_reward=True, sync=True)
+                      device=dev), norm_obs=True, norm_reward=True, sync=True if args.sync == "peer" else "nccl")
 env.reset()
 gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
 
@@ -61,8 +62,8 @@ else:
     same = torch.ones(1)
 if rank == 0:
     total = world * N * T
-    print(json.dumps({"config": "sdc-v1 rollout collection, device VecNormalize synchronised over NCCL, RolloutBuffer + GAE",
-                      "n_gpus": world, "envs_per_gpu": N, "n_steps": T, "env_steps_per_rollout": total,
+    print(json.dumps({"config": "sdc-v1 rollout collection, device VecNormalize synchronised over all ranks every step, RolloutBuffer + GAE",
+                      "n_gpus": world, "normaliser_sync": args.sync if world > 1 else "single rank", "envs_per_gpu": N, "n_steps": T, "env_steps_per_rollout": total,
                       "ms_per_rollout": float(ms.item()), "env_steps_per_s": total / (float(ms.item()) * 1e-3),
                       "normaliser_identical_on_all_ranks": bool(same.item() == 1.0)}), flush=True)
 if world > 1:
