@@ -112,3 +112,58 @@ def test_config4_rollout_collection_64m_env_steps():
     assert bool(torch.isfinite(env.obs_rms.mean).all()) and bool((env.obs_rms.var > 0).all())
     # unfinished envs have niter == number of steps since their last reset
     assert bool((venv.niter[:n] <= T).all())
+
+
+def _oracle_chunk(args):
+    lam, act = args
+    Q = collocation_matrix(5)
+    u, r = exact.reset(Q, 1.0, lam)
+    nit = np.zeros(lam.shape[0], np.int32)
+    o = exact.step("sdc-v0", Q, 1.0, lam, u, r, nit, r.copy(), act)
+    return u, r, nit, o["resnorm"], o["done"], o["err"]
+
+
+@pytest.mark.parametrize("sweep_mode", ["exact", "certified"])
+def test_config1_every_env_of_the_headline_batch_against_the_oracle(sweep_mode):
+    """config 1 at FULL size, every env (not a subsample): 2^20 sdc-v0 envs, M = 5, diagonal Q_delta, half of the batch
+    with uniform random actions (the benchmark workload), half near the MIN preconditioner (about half of those
+    converge).  The rounding-exact C oracle runs on all host cores (~10-30 s).  exact mode: every output bit-equal.
+    certified mode: niter / converged / err bit-equal, states within 1e-12 of ||u0|| + ||C|| ||u||."""
+    import multiprocessing as mp
+    import os
+
+    import torch
+    n, M = 1 << 20, 5
+    rng = np.random.default_rng(2027)
+    lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+    act = rng.uniform(-1, 1, (n, M))
+    x = np.diag(fixed_preconditioner("min", M))
+    act[n // 2:] = 2 * (x[None] + rng.uniform(-0.03, 0.03, (n - n // 2, M))) - 1
+    env = sdc_gym_b200.make("sdc-v0", num_envs=n, M=M, autoreset=False, sweep_mode=sweep_mode, **KW)
+    env.reset(lam=lam)
+    out = env.step_tensor(torch.as_tensor(act, device=env.device))
+    snap = env._snapshot()
+    cores = os.cpu_count() or 1
+    bounds = np.linspace(0, n, 4 * cores + 1).astype(int)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        parts = pool.map(_oracle_chunk, [(lam[a:b], act[a:b]) for a, b in zip(bounds, bounds[1:])])
+    u, r, nit, res, conv, err = (np.concatenate([p[k] for p in parts]) for k in range(6))
+    flags = out["flags"].cpu().numpy()
+    assert np.array_equal(out["niter"].cpu().numpy(), nit)
+    assert np.array_equal((flags & 2) != 0, conv) and np.array_equal((flags & 4) != 0, err)
+    assert 0.2 < conv.mean() < 0.3 and 0.05 < err.mean() < 0.2  # the workload exercises all three exits
+    gu, gr, gres = snap["obs"][:, 0], snap["obs"][:, 1], out["residual"].cpu().numpy()
+    if sweep_mode == "exact":
+        assert_same(gu, u)
+        assert_same(gr, r)
+        assert_same(gres, res)
+    else:
+        scale = 1.0 + 100.0 * np.abs(u).max(axis=1)
+        assert np.all(np.abs(gu - u).max(axis=1) <= 1e-12 * scale)
+        assert np.all(np.abs(gr - r).max(axis=1) <= 1e-12 * scale)
+        assert np.all(np.abs(gres - res) <= 1e-12 * scale)
+        nfb, _ = env.fallback_stats()
+        assert 0 < nfb < 0.1 * n
+        fb = env.fallback_list[:nfb].cpu().numpy()
+        assert_same(gu[fb], u[fb])  # re-run by the exact kernel: bit for bit
+        assert_same(gr[fb], r[fb])

@@ -193,26 +193,30 @@ def test_err_paths_nan_and_divergence():
 
 
 @pytest.mark.parametrize("prec_type", ["diag", "lower_diag", "lower_tri", "strictly_lower_tri"])
-@pytest.mark.parametrize("M", [3, 5, 7])
+@pytest.mark.parametrize("M", [2, 3, 4, 5, 6, 7, 8, 9])
 def test_spectral_radius_against_lapack(M, prec_type):
     from sdc_gym_b200.loss import SpectralRadiusLoss
     rng = np.random.default_rng(M)
     Q = collocation_matrix(M)
-    n, A = 2000, num_actions(M, prec_type)
+    n, A = (2000 if M in (3, 5, 7) else 600), num_actions(M, prec_type)
     lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
     for cplx in (False, True):
         hi = 0.6 if prec_type in ("diag", "lower_diag") else 0.2
         qd = rng.uniform(0, hi, (n, A)) + (1j * rng.uniform(-0.1, 0.1, (n, A)) if cplx else 0)
         loss = SpectralRadiusLoss(M, 1.0, prec_type)
         rho = loss.spectral_radii(lam.reshape(-1, 1), qd).cpu().numpy()
-        ref = np.empty(n)
+        ref, nk = np.empty(n), np.empty(n)
         for i in range(n):
             Qd = qdmat_from_output(qd[i], M, prec_type)
-            ref[i] = max(abs(np.linalg.eigvals(lam[i] * np.linalg.inv(np.eye(M) - lam[i] * Qd) @ (Q - Qd))))
-        # 1e-10 relative; badly conditioned K (huge non-normal triangular inverses) get the LAPACK
-        # noise floor eps * ||K||
-        assert np.all(np.abs(rho - ref) <= 1e-10 * ref + 1e-13 * ref.max()), np.max(np.abs(rho - ref) / ref)
-        assert abs(float(loss(lam, qd)) - ref.mean()) <= 1e-10 * ref.mean()
+            K = lam[i] * np.linalg.inv(np.eye(M) - lam[i] * Qd) @ (Q - Qd)
+            ref[i] = max(abs(np.linalg.eigvals(K)))
+            nk[i] = np.linalg.norm(K, 2)
+        # 1e-10 relative.  Strongly non-normal K (large M, strictly lower triangular Q_delta: ||K||_2 up
+        # to 1e8 with rho 1e7, cond(P) 1e8) - there LAPACK's own inv + eigvals are only good to ~1e-9 ||K||_2, and so
+        # is the comparison
+        tol = 1e-10 * ref + 1e-13 * ref.max() + np.where(nk > 10.0 * ref, 1e-9 * nk, 0.0)
+        assert np.all(np.abs(rho - ref) <= tol), np.max(np.abs(rho - ref) / ref)
+        assert abs(float(loss(lam, qd)) - ref.mean()) <= 1e-10 * ref.mean() + tol.mean()
 
 
 def test_spectral_radius_grid_and_fixed_prec():

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import sdc_gym_b200
 for name in ("sdc-v1", "sdc-v0"):
-    for n in (1, 8, 64, 1024, 16384):
+    for n in (1, 8, 64, 1024, 4096, 16384, 65536, 131072):
         env = sdc_gym_b200.make(name, num_envs=n, M=5, dt=1.0, restol=1e-10, seed=0,
                                 lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0])
         env.reset()
