@@ -269,6 +269,13 @@ int sdcgym_vecnorm_update_dist(int P, int64_t N, int64_t ld, const double* X, do
 int sdcgym_vecnorm_update_returns_dist(int64_t N, const double* reward, double gamma, double* returns, double* mean,
                                        double* var, double* count2, double* scratch, double* sums,
                                        const sdcgym_xchg* xchg, void* stream);
+/* Observation planes and the return plane in ONE launch (what a normalised training step needs): equivalent, bit for
+ * bit, to sdcgym_vecnorm_update followed by sdcgym_vecnorm_update_returns.  `scratch`: sdcgym_vecnorm_scratch_doubles(P + 1)
+ * doubles, zero-initialised once.  `xchg` == NULL: single rank; else the in-kernel exchange with slot_doubles >= 2P + 3. */
+int sdcgym_vecnorm_update_both(int P, int64_t N, int64_t ld, const double* X, const double* reward, double gamma,
+                               double* returns, double* obs_mean, double* obs_var, double* obs_count2, double* ret_mean,
+                               double* ret_var, double* ret_count2, double* scratch, double* sums_obs, double* sums_ret,
+                               const sdcgym_xchg* xchg, void* stream);
 /* device memory that other processes can map: cudaMalloc + zero fill + cudaIpcGetMemHandle / cudaIpcOpenMemHandle
  * (with peer access enabled lazily) / close / free */
 int sdcgym_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);

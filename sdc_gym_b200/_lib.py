@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdcgym.so")
+LIB_PATH = os.environ.get("SDCGYM_LIB") or os.path.join(_HERE, "libsdcgym.so")  # (SDCGYM_LIB: experiment builds)
 
 MAX_M = 9
 ABI_VERSION = 6
@@ -277,6 +277,9 @@ def load():
     L.sdcgym_xchg_bytes.restype = ctypes.c_size_t
     L.sdcgym_vecnorm_update_dist.argtypes = [ctypes.c_int, i64, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(Xchg), vp]
     L.sdcgym_vecnorm_update_returns_dist.argtypes = [i64, vp, dbl, vp, vp, vp, vp, vp, vp, ctypes.POINTER(Xchg), vp]
+    L.sdcgym_vecnorm_update_both.argtypes = [ctypes.c_int, i64, i64, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                             ctypes.POINTER(Xchg), vp]
+    L.sdcgym_vecnorm_update_both.restype = ctypes.c_int
     L.sdcgym_ipc_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]
     L.sdcgym_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
     L.sdcgym_ipc_close.argtypes = [vp]

@@ -235,7 +235,7 @@ SDCGYM_HD Cert cert_diag(const double (&Q)[M * M], double zr_d, double zi_d, con
     Cert c;
     cert_envelope<M, B>(Kr, Ki, dKrow, w, c.theta, c.G);
     // local error model and decision margin (units: absolute, eps folded in)
-    float a1 = 0.0f, a0 = 0.0f, a2 = 0.0f, iw = 0.0f, gam = 0.0f, amax = 0.0f;
+    float a1 = 0.0f, a0 = 0.0f, iw = 0.0f, gam = 0.0f, amax = 0.0f;
 #pragma unroll
     for (int m = 0; m < M; m++) {
         const float pw = pabs[m] / w[m];

@@ -74,6 +74,10 @@ static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& con
     return cudaSuccess;
 }
 
+#ifndef SDCGYM_FAST_MINB
+#define SDCGYM_FAST_MINB 4  // blocks per SM of the substitution-sweep kernel at M <= 5 (experiments: 5 -> 96 registers)
+#endif
+
 // SDCGYM_SWEEP_CERTIFIED, diagonal Q_delta, sdc-v0: certificate -> substitution sweeps -> exact kernel over the
 // fallback list (fast_kernels.cuh).  Three launches on the caller's stream.
 template <int V>
@@ -81,7 +85,7 @@ static cudaError_t launch_certified_diag(const StepParams<kM>& p, const FastWork
     cert_kernel<kM, V><<<(unsigned)((p.N + kCertBlock - 1) / kCertBlock), kCertBlock, 0, s>>>(p, fw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    constexpr int fminb = (kM <= 5) ? 4 : ((kM <= 7) ? 3 : 2);
+    constexpr int fminb = (kM <= 5) ? SDCGYM_FAST_MINB : ((kM <= 7) ? 3 : 2);
     fast_step_kernel<kM, V, fminb><<<(unsigned)((p.N + kFastBlock - 1) / kFastBlock), kFastBlock, 0, s>>>(p, fw);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;

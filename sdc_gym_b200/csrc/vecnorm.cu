@@ -469,6 +469,129 @@ extern "C" int sdcgym_gae(int T, int64_t N, const double* rewards, const double*
 
 extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2 + 2; }  // partials + the ticket word
 
+// ---- observation planes AND the return plane in one launch (grid.y = P + 1; plane P is the discounted return, advanced
+//      in the same pass).  Same slices, same trees, same merges as the two separate launches - bit-identical results -
+//      but one launch, one ticket and, with several ranks, ONE exchange for both statistics; the 64 blocks of the
+//      return plane no longer have the GPU to themselves. ----
+template <bool DIST>
+__global__ void __launch_bounds__(kAccThreads) update_both_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
+                                                                  const double* __restrict__ reward, double gamma,
+                                                                  double* __restrict__ ret, double* omean, double* ovar,
+                                                                  double* ocount, double* rmean, double* rvar,
+                                                                  double* rcount, double* __restrict__ partial,
+                                                                  double* __restrict__ osums, double* __restrict__ rsums,
+                                                                  unsigned int* ticket, const XchgDev xc) {
+    const int p = blockIdx.y;
+    const bool is_ret = (p == P);
+    const double s = is_ret ? rmean[0] : omean[p];
+    double a = 0.0, b = 0.0;
+    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
+    auto fetch = [&](int64_t i) {
+        if (is_ret) {
+            const double x = advance_return(ret[i], gamma, reward[i]);
+            ret[i] = x;
+            return x;
+        }
+        return X[(int64_t)p * ld + i];
+    };
+    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
+    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
+        double v[kAccBatch];
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) v[k] = fetch(i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
+    }
+    for (; i < N; i += stride) acc_one(fetch(i), s, a, b);
+    double2 r = block_sum2(a, b);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
+        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x * gridDim.y - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const double on = ocount[0], rn = rcount[0];
+    double batch = (double)N;
+    const int PP = P + 1;
+    __shared__ double fa[4 * SDCGYM_MAX_M + 1], fb[4 * SDCGYM_MAX_M + 1];
+    __syncthreads();
+    for (int q = threadIdx.x; q < PP; q += kAccThreads) {
+        double sa = 0.0, sb = 0.0;
+        for (int k = 0; k < kAccBlocks; k++) {
+            sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
+            sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+        }
+        fa[q] = sa;
+        fb[q] = sb;
+    }
+    __syncthreads();
+    if (DIST) {
+        const int parity = (int)(xc.seq & 1ull);
+        for (int q = threadIdx.x; q < PP; q += kAccThreads)
+            for (int rk = 0; rk < xc.world; rk++) {
+                double* slot = xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank);
+                slot[q] = fa[q];
+                slot[PP + q] = fb[q];
+            }
+        if (threadIdx.x == 0)
+            for (int rk = 0; rk < xc.world; rk++) xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank)[2 * PP] = batch;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < xc.world) {
+            volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
+            *remote = xc.seq;
+            volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
+            while (*mine != xc.seq) {
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        double* region = xc.peer[xc.rank];
+        batch = 0.0;
+        for (int rk = 0; rk < xc.world; rk++) batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, rk) + 2 * PP);
+        for (int q = threadIdx.x; q < PP; q += kAccThreads) {
+            double sa = 0.0, sb = 0.0;
+            for (int rk = 0; rk < xc.world; rk++) {
+                const double* slot = xchg_slot(region, xc.world, xc.stride, parity, rk);
+                sa += __ldcv(slot + q);
+                sb += __ldcv(slot + PP + q);
+            }
+            fa[q] = sa;
+            fb[q] = sb;
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < PP; q += kAccThreads) {
+        if (q < P) {
+            osums[q] = fa[q];
+            osums[P + q] = fb[q];
+            double m = omean[q], v = ovar[q];
+            if (batch > 0.0) rms_merge_one(on, batch, fa[q], fb[q], m, v);
+            omean[q] = m;
+            ovar[q] = v;
+        } else {
+            rsums[0] = fa[q];
+            rsums[1] = fb[q];
+            double m = rmean[0], v = rvar[0];
+            if (batch > 0.0) rms_merge_one(rn, batch, fa[q], fb[q], m, v);
+            rmean[0] = m;
+            rvar[0] = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        ocount[0] = on + batch;
+        ocount[1] = on + batch;
+        rcount[0] = rn + batch;
+        rcount[1] = rn + batch;
+        *ticket = 0u;
+    }
+}
+
 extern "C" int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
                                      double* count2, double* scratch, double* sums, void* stream) {
     if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
@@ -538,6 +661,32 @@ extern "C" int sdcgym_vecnorm_update_returns_dist(int64_t N, const double* rewar
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
     update_kernel<true, true><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
         1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket, d);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_update_both(int P, int64_t N, int64_t ld, const double* X, const double* reward, double gamma,
+                                          double* returns, double* obs_mean, double* obs_var, double* obs_count2,
+                                          double* ret_mean, double* ret_var, double* ret_count2, double* scratch,
+                                          double* sums_obs, double* sums_ret, const sdcgym_xchg* xchg, void* stream) {
+    if (P < 1 || P > 4 * SDCGYM_MAX_M || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if ((N > 0 && (!X || !reward || !returns)) || !obs_mean || !obs_var || !obs_count2 || !ret_mean || !ret_var ||
+        !ret_count2 || !scratch || !sums_obs || !sums_ret)
+        return SDCGYM_ENULL;
+    if (!xchg && N == 0) return 0;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)(P + 1) * kAccBlocks * 2);
+    const dim3 grid(kAccBlocks, P + 1);
+    if (xchg) {
+        XchgDev d{};
+        int rc = fill_xchg(xchg, P + 1, d);
+        if (rc) return rc;
+        update_both_kernel<true><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
+            P, N, ld, X, reward, gamma, returns, obs_mean, obs_var, obs_count2, ret_mean, ret_var, ret_count2, scratch,
+            sums_obs, sums_ret, ticket, d);
+    } else {
+        update_both_kernel<false><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
+            P, N, ld, X, reward, gamma, returns, obs_mean, obs_var, obs_count2, ret_mean, ret_var, ret_count2, scratch,
+            sums_obs, sums_ret, ticket, XchgDev{});
+    }
     return (int)cudaGetLastError();
 }
 

@@ -90,14 +90,14 @@ class VecNormalize:
         self.norm_terminal = torch.zeros_like(venv.S)
         self.current_norm_planes = self.norm_planes  # where the normalised current observation lives (see step_tensor)
         self.norm_reward_buf = torch.zeros(max(N, 1), dtype=torch.float64, device=dev)
-        nscr = self._L.sdcgym_vecnorm_scratch_doubles(self.P)
+        nscr = self._L.sdcgym_vecnorm_scratch_doubles(self.P + 1)  # (+1: the combined obs + returns launch)
         self._scratch = torch.zeros(nscr, dtype=torch.float64, device=dev)
         self._rscratch = torch.zeros(self._L.sdcgym_vecnorm_scratch_doubles(1), dtype=torch.float64, device=dev)
         self.fused_update = True  # single-rank: accumulate + merge in one launch (False: the three-kernel sequence)
         # several ranks: sync=True / "peer" folds the all-reduce of the moment sums into the statistics kernel (P2P
         # stores into every rank's exchange region over NVLink, csrc/vecnorm.cu update_kernel<.., DIST>);
         # sync="nccl" keeps accumulate -> ncclAllReduce -> merge
-        self._xchg_obs = self._xchg_ret = None
+        self._xchg_obs = self._xchg_ret = self._xchg_both = None
         # shifted sums of the observation planes and of the returns, contiguous so that a multi-rank step needs ONE
         # all-reduce for both statistics
         self._allsums = torch.zeros(2 * self.P + 1 + 3, dtype=torch.float64, device=dev)
@@ -134,7 +134,19 @@ class VecNormalize:
         if self._xchg_obs is None:
             self._xchg_obs = _dist_mod.PeerExchange(2 * self.P + 1)
             self._xchg_ret = _dist_mod.PeerExchange(3)
+            self._xchg_both = _dist_mod.PeerExchange(2 * self.P + 3)
         return True
+
+    def _update_both(self, N):
+        """Observation planes and discounted returns (advanced in the same pass) in ONE launch - with several ranks
+        also one in-kernel exchange for both statistics."""
+        v, o, r = self.venv, self.obs_rms, self.ret_rms
+        x = ctypes.byref(self._xchg_both.next()) if self._peer_mode() else None
+        _lib.check(self._L.sdcgym_vecnorm_update_both(
+            self.P, N, v.ld, v.S.data_ptr(), v.reward.data_ptr(), self.gamma, self.returns.data_ptr(),
+            o.mean.data_ptr(), o.var.data_ptr(), o.count2.data_ptr(), r.mean.data_ptr(), r.var.data_ptr(),
+            r.count2.data_ptr(), self._scratch.data_ptr(), self._sums.data_ptr(), self._rsums.data_ptr(), x,
+            self._stream()), "vecnorm_update_both")
 
     def _update(self, rms, planes_ptr, P, N, ld, sums):
         L, s = self._L, self._stream()
@@ -212,6 +224,10 @@ class VecNormalize:
         # step), merge both - instead of one collective per statistic
         peer = self.training and self._peer_mode()
         combined = self.training and self.norm_obs and self._multi_rank() and not peer
+        # single rank or in-kernel exchange, both statistics live: ONE launch for both
+        both = self.training and self.norm_obs and self.fused_update and (peer or not self._multi_rank())
+        if both:
+            self._update_both(N)
         if combined:
             self._accumulate(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
             _lib.check(L.sdcgym_vecnorm_returns(N, v.reward.data_ptr(), self.gamma, self.returns.data_ptr(), s), "returns")
@@ -223,7 +239,7 @@ class VecNormalize:
         if self.norm_obs:
             out = _StepOut(raw, self._normalized_terminal if self.venv.terminal is not None else None)
             out.pop("terminal", None)
-            if self.training and not combined:
+            if self.training and not combined and not both:
                 self._update(self.obs_rms, v.S.data_ptr(), self.P, N, v.ld, self._sums)
             dst = self.norm_planes
             if obs_out is not None:
@@ -238,7 +254,7 @@ class VecNormalize:
             out = dict(raw)
             out["obs_planes"] = v.S[:, :N]
         out["raw_reward"] = raw["reward"]
-        if combined:
+        if combined or both:
             pass  # return statistics already updated above
         elif peer:
             r = self.ret_rms

@@ -48,7 +48,9 @@ def _worker(rank, ws, port, tmp):
             v = sdist.make_sharded("sdc-v1", N_GLOBAL, **KW)
             envs[mode] = sdc_gym_b200.VecNormalize(v, norm_obs=True, norm_reward=True, sync=True if mode == "peer" else "nccl")
         res = {m: _run(e, lo, lo + cnt) for m, e in envs.items()}
-        assert envs["peer"]._xchg_obs is not None and envs["peer"]._xchg_obs.seq == STEPS + 1  # reset + steps
+        # reset: observation statistics alone; every step: ONE exchange for the observation and the return statistics
+        assert envs["peer"]._xchg_obs is not None and envs["peer"]._xchg_obs.seq == 1
+        assert envs["peer"]._xchg_both.seq == STEPS and envs["peer"]._xchg_ret.seq == 0
         assert envs["nccl"]._xchg_obs is None
         for (r1, o1), (r2, o2) in zip(res["peer"], res["nccl"]):
             assert torch.equal(r1, r2) and torch.equal(o1, o2)
@@ -66,6 +68,7 @@ def _worker(rank, ws, port, tmp):
             if e._xchg_obs is not None:
                 e._xchg_obs.close()
                 e._xchg_ret.close()
+                e._xchg_both.close()
     finally:
         dist.destroy_process_group()
 
