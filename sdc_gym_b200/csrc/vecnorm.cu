@@ -16,7 +16,10 @@
 
 namespace sdcgym {
 
-constexpr int kAccBlocks = 64, kAccThreads = 256, kAccBatch = 8;
+#ifndef SDCGYM_ACC_BATCH
+#define SDCGYM_ACC_BATCH 8
+#endif
+constexpr int kAccBlocks = 64, kAccThreads = 256, kAccBatch = SDCGYM_ACC_BATCH;  // (the batch only groups loads: the summation order is unchanged)
 
 __device__ __forceinline__ double2 block_sum2(double a, double b) {
     __shared__ double sa[kAccThreads / 32], sb[kAccThreads / 32];

@@ -943,7 +943,7 @@ class SDCVecEnv:
         """Checkpointable env state (device tensors cloned to host)."""
         N = self.num_envs
         return {k: getattr(self, k)[..., :N].cpu() for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr")} | {
-            "seed": int(self._desc.seed)}
+            "seed": int(self._desc.seed), "state_exact": bool(self._state_exact)}
 
     @_lib.on_device
     def load_state_dict(self, sd):
@@ -951,6 +951,9 @@ class SDCVecEnv:
         for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
             getattr(self, k)[..., :N].copy_(sd[k].to(self.device))
         self._desc.seed = int(sd["seed"])
+        # a checkpoint is a state the caller vouches for (like set_state): certified steps may start from it.  States
+        # saved after a certified step WITHOUT auto-reset carry that step's rounding-level approximation.
+        self._state_exact = bool(sd.get("state_exact", True))
         self._invalidate()
 
     @_lib.on_device
