@@ -146,6 +146,17 @@ __device__ __forceinline__ unsigned long long* xchg_flags(double* region, int wo
     return reinterpret_cast<unsigned long long*>(region + (size_t)2 * world * stride) + (size_t)parity * world;
 }
 
+// Wait for a peer's flag with a deadline (~20 s of SM clocks): a rank that never arrives (crashed process) must not
+// leave this kernel spinning forever.  Returns false on timeout; the caller then poisons the statistics with NaN so the
+// failure is visible in the very next normalised observation.
+__device__ __forceinline__ bool xchg_wait(volatile unsigned long long* flag, unsigned long long seq) {
+    const long long t0 = clock64();
+    while (*flag != seq) {
+        if (clock64() - t0 > 40000000000ll) return false;
+    }
+    return true;
+}
+
 template <bool RETURNS, bool DIST>
 __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
                                                              const double* __restrict__ reward, double gamma,
@@ -212,15 +223,17 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
             volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
             *remote = xc.seq;
         }
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
         if (threadIdx.x < xc.world) {
             volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
-            while (*mine != xc.seq) {
-            }
+            if (!xchg_wait(mine, xc.seq)) timed_out = 1;
         }
         __threadfence_system();
         __syncthreads();
         double* region = xc.peer[xc.rank];
-        batch = 0.0;
+        batch = timed_out ? CUDART_NAN : 0.0;
         for (int r = 0; r < xc.world; r++)
             batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, r) + 2 * P);
         for (int q = threadIdx.x; q < P; q += kAccThreads) {
@@ -233,7 +246,7 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
             sums[q] = sa;
             sums[P + q] = sb;
             double m = mean[q], v = var[q];
-            if (batch > 0.0) rms_merge_one(n, batch, sa, sb, m, v);
+            if (batch > 0.0 || batch != batch) rms_merge_one(n, batch, sa, sb, m, v);  // (NaN batch: a peer timed out)
             mean[q] = m;
             var[q] = v;
         }
@@ -545,17 +558,19 @@ __global__ void __launch_bounds__(kAccThreads) update_both_kernel(int P, int64_t
             for (int rk = 0; rk < xc.world; rk++) xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank)[2 * PP] = batch;
         __threadfence_system();
         __syncthreads();
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
         if (threadIdx.x < xc.world) {
             volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
             *remote = xc.seq;
             volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
-            while (*mine != xc.seq) {
-            }
+            if (!xchg_wait(mine, xc.seq)) timed_out = 1;
         }
         __threadfence_system();
         __syncthreads();
         double* region = xc.peer[xc.rank];
-        batch = 0.0;
+        batch = timed_out ? CUDART_NAN : 0.0;
         for (int rk = 0; rk < xc.world; rk++) batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, rk) + 2 * PP);
         for (int q = threadIdx.x; q < PP; q += kAccThreads) {
             double sa = 0.0, sb = 0.0;
@@ -574,14 +589,14 @@ __global__ void __launch_bounds__(kAccThreads) update_both_kernel(int P, int64_t
             osums[q] = fa[q];
             osums[P + q] = fb[q];
             double m = omean[q], v = ovar[q];
-            if (batch > 0.0) rms_merge_one(on, batch, fa[q], fb[q], m, v);
+            if (batch > 0.0 || batch != batch) rms_merge_one(on, batch, fa[q], fb[q], m, v);  // (NaN: a peer timed out)
             omean[q] = m;
             ovar[q] = v;
         } else {
             rsums[0] = fa[q];
             rsums[1] = fb[q];
             double m = rmean[0], v = rvar[0];
-            if (batch > 0.0) rms_merge_one(rn, batch, fa[q], fb[q], m, v);
+            if (batch > 0.0 || batch != batch) rms_merge_one(rn, batch, fa[q], fb[q], m, v);
             rmean[0] = m;
             rvar[0] = v;
         }

@@ -151,7 +151,7 @@ def test_config1_every_env_of_the_headline_batch_against_the_oracle(sweep_mode):
     flags = out["flags"].cpu().numpy()
     assert np.array_equal(out["niter"].cpu().numpy(), nit)
     assert np.array_equal((flags & 2) != 0, conv) and np.array_equal((flags & 4) != 0, err)
-    assert 0.2 < conv.mean() < 0.3 and 0.05 < err.mean() < 0.2  # the workload exercises all three exits
+    assert 0.1 < conv.mean() < 0.3 and 0.05 < err.mean() < 0.2  # the workload exercises all three exits
     gu, gr, gres = snap["obs"][:, 0], snap["obs"][:, 1], out["residual"].cpu().numpy()
     if sweep_mode == "exact":
         assert_same(gu, u)
