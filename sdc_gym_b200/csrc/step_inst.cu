@@ -7,9 +7,14 @@
 #include "step_params.cuh"
 #include "team_kernels.cuh"
 #include "fast_kernels.cuh"
+#include "stream_kernels.cuh"
 
 #ifndef SDCGYM_M
 #error "compile with -DSDCGYM_M=<2..9>"
+#endif
+
+#ifndef SDCGYM_STREAM_MINB
+#define SDCGYM_STREAM_MINB 2  // blocks (of 256 threads) per SM of the streaming sdc-v1 kernel
 #endif
 
 #define SDCGYM_CAT_(a, b) a##b
@@ -21,6 +26,22 @@ constexpr int kM = SDCGYM_M;
 constexpr int kHoldDiag = HoldPolicy<kM>::diag;
 constexpr int kHoldDense = HoldPolicy<kM>::dense;
 
+
+// opt-in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute, remembered per (instantiation, device)
+template <typename K>
+static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& configured) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = (dev >= 0 && dev < 64) ? (uint64_t(1) << dev) : 0;
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
+}
 
 template <int KIND, int V, bool DENSE>
 static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
@@ -34,6 +55,49 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
         }
     }
     constexpr bool kStep = (KIND == SDCGYM_ENV_STEP);
+    if constexpr (kStep && !DENSE && HoldPolicy<kM>::step == 0 && kM <= 7) {
+        // sdc-v1, diagonal Q_delta, large batch: persistent blocks with the next tile's inputs in flight as bulk
+        // asynchronous copies (stream_kernels.cuh); the tail that does not fill a tile takes the plain kernel below
+        static const bool no_stream = getenv("SDCGYM_NO_STREAM") != nullptr;  // A/B switch for experiments
+        const int w = p.is_complex ? 2 : 1;
+        const bool has_act = p.prec_type != SDCGYM_PREC_FIXED;
+        const bool rows_ok = !has_act || (p.a_cs == w && p.a_es == (int64_t)kM * w &&
+                                          (reinterpret_cast<uintptr_t>(p.action) & 15u) == 0);
+        const bool aligned = ((reinterpret_cast<uintptr_t>(p.lam) | reinterpret_cast<uintptr_t>(p.S) |
+                               reinterpret_cast<uintptr_t>(p.resnorm) | reinterpret_cast<uintptr_t>(p.niter) |
+                               reinterpret_cast<uintptr_t>(p.episodes) | reinterpret_cast<uintptr_t>(p.rng_ctr)) & 15u) == 0 &&
+                             (p.ld % 2) == 0;
+        const int64_t tiles = p.N / kStreamTile;
+        if (!no_stream && p.old_states == nullptr && rows_ok && aligned && tiles >= 148 * 2 &&
+            p.strategy == SDCGYM_REW_ITERATION_ONLY) {  // (the other rewards are FP64-latency bound: see stream_kernels.cuh)
+            constexpr int sminb = SDCGYM_STREAM_MINB > 0 ? SDCGYM_STREAM_MINB : HoldPolicy<kM>::step_minb;
+            constexpr size_t smem = StreamStage<kM>::bytes;
+            auto kern = step_stream_kernel<kM, V, sminb>;
+            static std::atomic<uint64_t> configured{0};
+            cudaError_t e = opt_in_smem(kern, smem, configured);
+            if (e != cudaSuccess) return e;
+            const int64_t want = (int64_t)148 * sminb;  // persistent: every SM at its resident block count
+            const unsigned grid = (unsigned)(tiles < want ? tiles : want);
+            kern<<<grid, kStreamTile, smem, s>>>(p, tiles, has_act ? kM * w * 8 : 0);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            const int64_t done = tiles * kStreamTile;
+            if (done == p.N) return cudaSuccess;
+            // tail: the same envs through the plain kernel, addressed by offset pointers
+            StepParams<kM> q = p;
+            q.N = p.N - done;
+            q.lam += done; q.S += done; q.resnorm += done; q.niter += done; q.episodes += done; q.rng_ctr += done;
+            if (q.action) q.action += done * p.a_es;
+            if (q.reward) q.reward += done;
+            if (q.flags) q.flags += done;
+            if (q.info_res) q.info_res += done;
+            if (q.info_niter) q.info_niter += done;
+            if (q.info_lam) q.info_lam += 2 * done;
+            if (q.term) q.term += done;
+            q.env_offset += done;
+            return launch_step<KIND, V, DENSE>(q, s);
+        }
+    }
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);
     constexpr int minb = DENSE ? HoldPolicy<kM>::dense_minb : (kStep ? HoldPolicy<kM>::step_minb : HoldPolicy<kM>::diag_minb);
     constexpr int block = DENSE ? HoldPolicy<kM>::dense_block : ((!kStep) ? HoldPolicy<kM>::diag_block : kBlock);
@@ -56,22 +120,6 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     }
     kernel<<<(unsigned)((p.N + block - 1) / block), block, smem, s>>>(p);
     return cudaGetLastError();
-}
-
-// opt-in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute, remembered per (instantiation, device)
-template <typename K>
-static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& configured) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    const uint64_t bit = (dev >= 0 && dev < 64) ? (uint64_t(1) << dev) : 0;
-    if (!(configured.load(std::memory_order_relaxed) & bit)) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured.fetch_or(bit, std::memory_order_relaxed);
-    }
-    return cudaSuccess;
 }
 
 #ifndef SDCGYM_FAST_MINB

@@ -50,6 +50,22 @@ struct StepParams {
     double log_restol_nf;  // math.log(restol * norm_factor) (sdc_env.py:346), evaluated once on the host
 };
 
+// Where a step reads its per-env inputs from.  Default (nullptr): the global planes of StepParams, element `i`.  The
+// streaming sdc-v1 kernel (stream_kernels.cuh) stages a whole tile of envs in shared memory with bulk asynchronous
+// copies and points these at the staged copy (plane stride `ld`, element `i` within the tile); outputs always go to
+// the global planes.
+struct StepInputs {
+    const double* lam;        // [2][ld]
+    const double* S;          // [4M][ld]
+    const double* resnorm;    // [ld]
+    const int32_t* niter;     // [ld]
+    const int32_t* episodes;  // [ld]
+    const uint32_t* rng_ctr;  // [ld]
+    const double* action;     // env-major rows, same strides as StepParams::a_es / a_cs; nullptr: no actions
+    int64_t ld;
+    int64_t i;
+};
+
 // ---- C = eye(M) - (lam*dt)*Q, one row (sdc_env.py:302-304; Appendix A step 2).  0 - x is written -x
 //      (differs only in the sign of an exact zero). ----
 template <int M>
@@ -274,17 +290,28 @@ SDCGYM_HD cplx ld_pair(const cplx* p) {
 #endif
 }
 
-template <int M, int KIND, int V, bool DENSE, int HOLD>
+struct NoAfterLoads {
+    SDCGYM_HD void operator()() const {}
+};
+
+// `after_loads` runs once every input of the env sits in registers (non-dense kernels): the streaming kernel releases
+// its shared-memory stage there and starts the next tile's copies.
+template <int M, int KIND, int V, bool DENSE, int HOLD, class AfterLoads = NoAfterLoads>
 SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1,
-                        cplx* pside = nullptr, const int pstride = 1) {
+                        cplx* pside = nullptr, const int pstride = 1, const StepInputs* in = nullptr,
+                        AfterLoads after_loads = AfterLoads()) {
     const bool valid = tid < p.N;
     const int64_t i = valid ? tid : p.N - 1;
     const int64_t ld = p.ld;
+    // input side (see StepInputs): staged tile or the global planes
+    const double* const in_lam = in ? in->lam : p.lam;
+    const double* const in_S = in ? in->S : p.S;
+    const int64_t ild = in ? in->ld : ld, ii = in ? in->i : i;
 
     // ---- phase 0: every global load of this env is issued here, in one basic block, so that a single DRAM round trip
     //      covers them all (placed at their uses they end up behind the branches of the division slow paths, one
     //      exposed latency each) ----
-    double lr = p.lam[i], li = p.lam[ld + i];
+    double lr = in_lam[ii], li = in_lam[ild + ii];
     double araw[DENSE ? 1 : M], aimg[DENSE ? 1 : M];
     if (!DENSE) {
 #pragma unroll
@@ -292,8 +319,13 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             araw[k] = 0.0;
             aimg[k] = 0.0;
             if (p.prec_type != SDCGYM_PREC_FIXED) {
-                araw[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs);
-                if (p.is_complex) aimg[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
+                if (in) {  // staged rows (shared memory: plain loads)
+                    araw[k] = in->action[ii * p.a_es + k * p.a_cs];
+                    if (p.is_complex) aimg[k] = in->action[ii * p.a_es + k * p.a_cs + 1];
+                } else {
+                    araw[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs);
+                    if (p.is_complex) aimg[k] = ld_ro(p.action + i * p.a_es + k * p.a_cs + 1);
+                }
             }
         }
     }
@@ -301,18 +333,18 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     auto load_state = [&]() {
 #pragma unroll
         for (int m = 0; m < M; m++) {
-            ur[m] = p.S[(2 * m) * ld + i];
-            ui[m] = p.S[(2 * m + 1) * ld + i];
-            rr[m] = p.S[(2 * M + 2 * m) * ld + i];
-            ri[m] = p.S[(2 * M + 2 * m + 1) * ld + i];
+            ur[m] = in_S[(2 * m) * ild + ii];
+            ui[m] = in_S[(2 * m + 1) * ild + ii];
+            rr[m] = in_S[(2 * M + 2 * m) * ild + ii];
+            ri[m] = in_S[(2 * M + 2 * m + 1) * ild + ii];
         }
     };
     if (!DENSE) load_state();  // the dense kernels need the registers for the inverse first
-    double nr_old = p.resnorm[i];
-    int it = (KIND == SDCGYM_ENV_STEP) ? p.niter[i] : 0;
+    double nr_old = in ? in->resnorm[ii] : p.resnorm[i];
+    int it = (KIND == SDCGYM_ENV_STEP) ? (in ? in->niter[ii] : p.niter[i]) : 0;
     // the auto-reset needs these at the very end
-    int32_t ep_old = p.autoreset ? p.episodes[i] : 0;
-    uint32_t ctr_old = p.autoreset ? p.rng_ctr[i] : 0u;
+    int32_t ep_old = p.autoreset ? (in ? in->episodes[ii] : p.episodes[i]) : 0;
+    uint32_t ctr_old = p.autoreset ? (in ? in->rng_ctr[ii] : p.rng_ctr[i]) : 0u;
 #ifdef __CUDA_ARCH__
     // consume everything here: keeps the loads above this point.  (Not for the dense kernels: they load the Q_delta
     // entries next and a barrier here would only add a second exposed round trip - measured 20 % slower at M = 3.)
@@ -324,6 +356,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         for (int m = 0; m < M; m++) asm volatile("" : "+d"(ur[m]), "+d"(ui[m]), "+d"(rr[m]), "+d"(ri[m]));
     }
 #endif
+    if (!DENSE) after_loads();
     const double zr = dmul(lr, p.dt), zi = dmul(li, p.dt);
 
     // ---- preconditioner inverse ----
