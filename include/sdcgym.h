@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 6 /* 5: sweep_mode + work buffers in sdcgym_state; 6: in-kernel peer-memory statistics exchange */
+#define SDCGYM_ABI_VERSION 7 /* 5: sweep_mode + work buffers in sdcgym_state; 6: in-kernel peer-memory statistics exchange; 7: sdcgym_state.norm_init */
 #define SDCGYM_MAX_M 9
 #define SDCGYM_CERT_PLANES 8
 
@@ -127,6 +127,10 @@ typedef struct sdcgym_state {
     int32_t* niter;    /* [ld] */
     int32_t* episodes; /* [ld]  num_episodes (sdc_env.py:81,276) */
     uint32_t* rng_ctr; /* [ld]  number of lambda draws made so far */
+    double* norm_init; /* [ld] or NULL: ||initial residual of the running episode||_inf (scaled by norm_factor), written by
+                        * every reset / auto-reset.  The `residual_change` reward divides by its logarithm
+                        * (sdc_env.py:337-350); with the plane the step reads 8 bytes instead of re-deriving the initial
+                        * state and its norm (~250 FP64 instructions per env-step).  Same bits either way. */
     /* work buffers of SDCGYM_SWEEP_CERTIFIED (NULL otherwise): */
     float* cert;            /* [SDCGYM_CERT_PLANES][ld] per-env certificate constants, rewritten by every step */
     int32_t* fallback_list; /* [N] indices of the envs the exact kernel re-ran in the last step */

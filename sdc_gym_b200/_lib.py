@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDCGYM_LIB") or os.path.join(_HERE, "libsdcgym.so")  # (SDCGYM_LIB: experiment builds)
 
 MAX_M = 9
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -79,6 +79,7 @@ class State(ctypes.Structure):
         ("niter", ctypes.c_void_p),
         ("episodes", ctypes.c_void_p),
         ("rng_ctr", ctypes.c_void_p),
+        ("norm_init", ctypes.c_void_p),
         ("cert", ctypes.c_void_p),
         ("fallback_list", ctypes.c_void_p),
         ("fallback_count", ctypes.c_void_p),

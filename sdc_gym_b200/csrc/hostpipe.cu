@@ -300,6 +300,7 @@ static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdc
         sdcgym_state s2 = *st;
         s2.N = n;
         s2.lam += lo; s2.S += lo; s2.resnorm += lo; s2.niter += lo; s2.episodes += lo; s2.rng_ctr += lo;
+        if (s2.norm_init) s2.norm_init += lo;
         if (s2.cert) s2.cert += lo;                    // certified sweep mode: per-chunk certificate planes and fallback list
         if (s2.fallback_list) s2.fallback_list += lo;  // (indices are local to the chunk)
         sdcgym_step_io io = *dev;
@@ -543,6 +544,7 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
         sdcgym_state s2 = *st;
         s2.N = n;
         s2.lam += lo; s2.S += lo; s2.resnorm += lo; s2.niter += lo; s2.episodes += lo; s2.rng_ctr += lo;
+        if (s2.norm_init) s2.norm_init += lo;
         if (s2.cert) s2.cert += lo;                    // certified sweep mode: per-chunk certificate planes and fallback list
         if (s2.fallback_list) s2.fallback_list += lo;  // (indices are local to the chunk)
         sdcgym_step_io io2 = io;

@@ -58,7 +58,8 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     if constexpr (kStep && !DENSE && HoldPolicy<kM>::step == 0 && kM <= 7) {
         // sdc-v1, diagonal Q_delta, large batch: persistent blocks with the next tile's inputs in flight as bulk
         // asynchronous copies (stream_kernels.cuh); the tail that does not fill a tile takes the plain kernel below
-        static const bool no_stream = getenv("SDCGYM_NO_STREAM") != nullptr;  // A/B switch for experiments
+        static const bool no_stream = getenv("SDCGYM_NO_STREAM") != nullptr;  // A/B switches for experiments
+        static const bool stream_all = getenv("SDCGYM_STREAM_ALL") != nullptr;
         const int w = p.is_complex ? 2 : 1;
         const bool has_act = p.prec_type != SDCGYM_PREC_FIXED;
         const bool rows_ok = !has_act || (p.a_cs == w && p.a_es == (int64_t)kM * w &&
@@ -69,7 +70,7 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
                              (p.ld % 2) == 0;
         const int64_t tiles = p.N / kStreamTile;
         if (!no_stream && p.old_states == nullptr && rows_ok && aligned && tiles >= 148 * 2 &&
-            p.strategy == SDCGYM_REW_ITERATION_ONLY) {  // (the other rewards are FP64-latency bound: see stream_kernels.cuh)
+            (p.strategy == SDCGYM_REW_ITERATION_ONLY || stream_all)) {  // (the other rewards are FP64-latency bound: see stream_kernels.cuh)
             constexpr int sminb = SDCGYM_STREAM_MINB > 0 ? SDCGYM_STREAM_MINB : HoldPolicy<kM>::step_minb;
             constexpr size_t smem = StreamStage<kM>::bytes;
             auto kern = step_stream_kernel<kM, V, sminb>;
@@ -87,6 +88,7 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
             StepParams<kM> q = p;
             q.N = p.N - done;
             q.lam += done; q.S += done; q.resnorm += done; q.niter += done; q.episodes += done; q.rng_ctr += done;
+            if (q.norm_init) q.norm_init += done;
             if (q.action) q.action += done * p.a_es;
             if (q.reward) q.reward += done;
             if (q.flags) q.flags += done;

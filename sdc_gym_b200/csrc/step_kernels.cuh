@@ -31,6 +31,7 @@ struct StepParams {
     int32_t* niter;
     int32_t* episodes;
     uint32_t* rng_ctr;
+    double* norm_init;  // optional plane: scaled norm of the episode's initial residual (sdcgym_state.norm_init)
     const double* action;
     int64_t a_es, a_cs;
     double* reward;
@@ -61,6 +62,7 @@ struct StepInputs {
     const int32_t* niter;     // [ld]
     const int32_t* episodes;  // [ld]
     const uint32_t* rng_ctr;  // [ld]
+    const double* norm_init;  // [ld] or nullptr
     const double* action;     // env-major rows, same strides as StepParams::a_es / a_cs; nullptr: no actions
     int64_t ld;
     int64_t i;
@@ -148,6 +150,25 @@ SDCGYM_HD void store_column(double* __restrict__ os, int64_t e, int max_iters, i
     }
 }
 
+template <int M>
+SDCGYM_HD double scaled_inf_norm(const double (&vr)[M], const double (&vi)[M], double nf) {
+    double tr[M], ti[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) {
+        tr[m] = dmul(vr[m], nf);  // numpy complex * real scalar
+        ti[m] = dmul(vi[m], nf);
+    }
+    // same value as inf_norm (abs(v).max()): numpy's |.| is evaluated only for the node that provably attains the
+    // maximum (one division + square root instead of M of them)
+    return inf_norm_fast<M>(tr, ti);
+}
+
+// the norm_init plane (when present) is written by every reset: ||r0||inf scaled by norm_factor.  `plain` is ||r0||inf.
+template <int M>
+SDCGYM_HD void store_norm_init(const StepParams<M>& p, int64_t i, const double (&rr)[M], const double (&ri)[M], double plain) {
+    if (p.norm_init) p.norm_init[i] = (p.norm_factor == 1.0) ? plain : scaled_inf_norm<M>(rr, ri, p.norm_factor);
+}
+
 // =====================================================================================================
 // reset kernel
 // =====================================================================================================
@@ -173,7 +194,9 @@ SDCGYM_HD void reset_one(const StepParams<M>& p, int64_t i) {
     double ur[M], ui[M], rr[M], ri[M];
     initial_state<M, V>(p.Q, zr, zi, ur, ui, rr, ri);
     store_state<M>(p.S, p.ld, i, ur, ui, rr, ri);
-    p.resnorm[i] = inf_norm_fast<M>(rr, ri);
+    const double n0 = inf_norm_fast<M>(rr, ri);
+    p.resnorm[i] = n0;
+    store_norm_init<M>(p, i, rr, ri, n0);
     if (p.old_states) {
         store_column<M>(p.old_states, i, p.max_iters, 0, ur, ui, rr, ri);
         double* base = p.old_states + (size_t)i * (2 * M) * p.max_iters * 2;
@@ -188,19 +211,6 @@ SDCGYM_HD void reset_one(const StepParams<M>& p, int64_t i) {
 // =====================================================================================================
 // rewards (sdc_env.py:334-463), evaluated once per env after the sweeps
 // =====================================================================================================
-template <int M>
-SDCGYM_HD double scaled_inf_norm(const double (&vr)[M], const double (&vi)[M], double nf) {
-    double tr[M], ti[M];
-#pragma unroll
-    for (int m = 0; m < M; m++) {
-        tr[m] = dmul(vr[m], nf);  // numpy complex * real scalar
-        ti[m] = dmul(vi[m], nf);
-    }
-    // same value as inf_norm (abs(v).max()): numpy's |.| is evaluated only for the node that provably attains the
-    // maximum (one division + square root instead of M of them)
-    return inf_norm_fast<M>(tr, ti);
-}
-
 template <int M>
 SDCGYM_HD_NOINLINE double reward_func(int strategy, double sp, double rw, double nf, double restol, int max_iters,
                                            double norm_old_scaled, double norm_init_scaled, const double (&rr)[M],
@@ -345,6 +355,10 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     // the auto-reset needs these at the very end
     int32_t ep_old = p.autoreset ? (in ? in->episodes[ii] : p.episodes[i]) : 0;
     uint32_t ctr_old = p.autoreset ? (in ? in->rng_ctr[ii] : p.rng_ctr[i]) : 0u;
+    // cached ||initial residual|| of the episode (residual_change reward); NaN marks "not cached: re-derive"
+    double ninit_cached = d_nan();
+    if (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE && p.norm_init)
+        ninit_cached = (in && in->norm_init) ? in->norm_init[ii] : p.norm_init[i];
 #ifdef __CUDA_ARCH__
     // consume everything here: keeps the loads above this point.  (Not for the dense kernels: they load the Q_delta
     // entries next and a barrier here would only add a second exposed round trip - measured 20 % slower at M = 3.)
@@ -666,10 +680,14 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     } else {
         double norm_init_scaled = 0.0;
         if (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE) {
-            // initial residual of the episode is a function of lambda only: recompute it
-            double tu[M], tv[M], ir[M], ii[M];
-            initial_state<M, V>(p.Q, zr, zi, tu, tv, ir, ii);
-            norm_init_scaled = scaled_inf_norm<M>(ir, ii, p.norm_factor);
+            if (p.norm_init) {
+                norm_init_scaled = ninit_cached;  // written by the reset of this episode (same function, same bits)
+            } else {
+                // initial residual of the episode is a function of lambda only: recompute it
+                double tu[M], tv[M], ir[M], ii2[M];
+                initial_state<M, V>(p.Q, zr, zi, tu, tv, ir, ii2);
+                norm_init_scaled = scaled_inf_norm<M>(ir, ii2, p.norm_factor);
+            }
             if (KIND == SDCGYM_ENV_FULL) norm_old_scaled = norm_init_scaled;  // reward_func(initial_residual, ...)
         }
         rew = reward_func<M>(p.strategy, p.step_penalty, p.residual_weight, p.norm_factor, p.restol, p.max_iters,
@@ -706,7 +724,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         const double nzr = dmul(nlr, p.dt), nzi = dmul(nli, p.dt);
         initial_state<M, V>(p.Q, nzr, nzi, ur, ui, rr, ri);
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);
-        p.resnorm[i] = inf_norm_fast<M>(rr, ri);
+        const double n0 = inf_norm_fast<M>(rr, ri);
+        p.resnorm[i] = n0;
+        store_norm_init<M>(p, i, rr, ri, n0);
         p.niter[i] = 0;
     } else {
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);

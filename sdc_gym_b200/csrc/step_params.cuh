@@ -18,6 +18,7 @@ inline void fill_params(StepParams<M>& p, const sdcgym_env_desc* d, const sdcgym
     p.niter = st->niter;
     p.episodes = st->episodes;
     p.rng_ctr = st->rng_ctr;
+    p.norm_init = st->norm_init;
     p.action = nullptr;
     p.a_es = p.a_cs = 0;
     p.reward = nullptr;

@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
     // ---- DummyVecEnv auto-reset: every lane derives the team's new lambda and its own component of the new
     //      residual r = u0 - C @ 1; the team-wide vector (for the new ||r||inf) goes through the exchange buffer.
     //      Computed for every team (the exchange is warp-wide), used by the ones that are done. ----
-    double nlr = 0.0, nli = 0.0, nrr = 0.0, nri = 0.0, nres = 0.0;
+    double nlr = 0.0, nli = 0.0, nrr = 0.0, nri = 0.0, nres = 0.0, ninit = 0.0;
     const int32_t ep = ep_old + 1;
     if (p.autoreset) {
         draw_lambda<M>(p, i, ctr_old, ep, nlr, nli);
@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
         __syncwarp();  // every lane has read the last residual exchange
         exchange(xr, nrr, nri, Ir, Ii);
         nres = inf_norm_fast<M>(Ir, Ii);
+        ninit = (p.norm_init && p.norm_factor != 1.0) ? scaled_inf_norm<M>(Ir, Ii, p.norm_factor) : nres;
     }
     if (!valid) return;
 
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
             p.lam[i] = nlr;
             p.lam[ld + i] = nli;
             p.resnorm[i] = nres;
+            if (p.norm_init) p.norm_init[i] = ninit;
             p.niter[i] = 0;
         }
     } else {

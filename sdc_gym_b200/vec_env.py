@@ -324,6 +324,8 @@ class SDCVecEnv:
             self.niter = torch.zeros(self.ld, dtype=torch.int32, device=dev)
             self.episodes = torch.zeros(self.ld, dtype=torch.int32, device=dev)
             self.rng_ctr = torch.zeros(self.ld, dtype=torch.int32, device=dev)
+            # ||initial residual|| of the running episode, kept for the residual_change reward (sdcgym_state.norm_init)
+            self.norm_init = torch.zeros(self.ld, dtype=f64, device=dev)
             # results of a step: ONE device block (include/sdcgym.h: sdcgym_block_layout) whose host twin is what
             # `step` hands out, so a step's results leave the GPU in a single transfer; the per-array tensors below
             # are views of it
@@ -428,6 +430,7 @@ class SDCVecEnv:
         st.niter = self.niter.data_ptr() + 4 * start
         st.episodes = self.episodes.data_ptr() + 4 * start
         st.rng_ctr = self.rng_ctr.data_ptr() + 4 * start
+        st.norm_init = self.norm_init.data_ptr() + 8 * start
         if self._certified:
             st.cert = self.cert.data_ptr() + 4 * start
             st.fallback_list = self.fallback_list.data_ptr() + 4 * start
@@ -548,6 +551,21 @@ class SDCVecEnv:
         return self._snap
 
     @_lib.on_device
+    def _rebuild_norm_init(self):
+        """norm_init of the running episodes from their lambdas (reset kernel on scratch planes)."""
+        torch = _torch()
+        scratch = dict(lam=torch.empty_like(self.lam), S=torch.empty_like(self.S), resnorm=torch.empty_like(self.resnorm),
+                       niter=torch.empty_like(self.niter), episodes=torch.zeros_like(self.episodes),
+                       rng_ctr=torch.zeros_like(self.rng_ctr))
+        st = _lib.State()
+        st.N, st.ld = self.num_envs, self.ld
+        for k, t in scratch.items():
+            setattr(st, k, t.data_ptr())
+        st.norm_init = self.norm_init.data_ptr()
+        _lib.check(self._L.sdcgym_reset(ctypes.byref(self._desc), ctypes.byref(st), self.lam.data_ptr(), None, None,
+                                        self._stream()), "sdcgym_reset")
+        _torch().cuda.current_stream(self.device).synchronize()
+
     def _initial_residuals(self):
         if self._init_res is None:
             # r0 is a function of lambda only: run the reset kernel on scratch planes with lambda injected
@@ -942,7 +960,8 @@ class SDCVecEnv:
     def state_dict(self):
         """Checkpointable env state (device tensors cloned to host)."""
         N = self.num_envs
-        return {k: getattr(self, k)[..., :N].cpu() for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr")} | {
+        return {k: getattr(self, k)[..., :N].cpu() for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr",
+                                                             "norm_init")} | {
             "seed": int(self._desc.seed), "state_exact": bool(self._state_exact)}
 
     @_lib.on_device
@@ -950,6 +969,10 @@ class SDCVecEnv:
         N = self.num_envs
         for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
             getattr(self, k)[..., :N].copy_(sd[k].to(self.device))
+        if "norm_init" in sd:
+            self.norm_init[:N].copy_(sd["norm_init"].to(self.device))
+        else:  # a checkpoint written before the plane existed: re-derive it from the lambdas
+            self._rebuild_norm_init()
         self._desc.seed = int(sd["seed"])
         # a checkpoint is a state the caller vouches for (like set_state): certified steps may start from it.  States
         # saved after a certified step WITHOUT auto-reset carry that step's rounding-level approximation.

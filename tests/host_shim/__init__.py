@@ -90,6 +90,7 @@ class ShimBatch:
         self.niter = np.zeros(ld, np.int32)
         self.episodes = np.zeros(ld, np.int32)
         self.rng_ctr = np.zeros(ld, np.uint32)
+        self.norm_init = np.zeros(ld)  # cached ||initial residual|| (sdcgym_state.norm_init); None: re-derived per step
         self.reward = np.zeros(ld)
         self.flags = np.zeros(ld, np.uint8)
         self.info_res = np.zeros(ld)
@@ -108,6 +109,7 @@ class ShimBatch:
         st.N, st.ld = self.n, self.ld
         for k in ("lam", "S", "resnorm", "niter", "episodes", "rng_ctr"):
             setattr(st, k, getattr(self, k).ctypes.data)
+        st.norm_init = None if self.norm_init is None else self.norm_init.ctypes.data
         st.cert, st.fallback_list = self.cert.ctypes.data, self.fallback_list.ctypes.data
         st.fallback_count = self.fallback_count.ctypes.data
         return st
