@@ -70,7 +70,8 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
                              (p.ld % 2) == 0;
         const int64_t tiles = p.N / kStreamTile;
         if (!no_stream && p.old_states == nullptr && rows_ok && aligned && tiles >= 148 * 2 &&
-            (p.strategy == SDCGYM_REW_ITERATION_ONLY || stream_all)) {  // (the other rewards are FP64-latency bound: see stream_kernels.cuh)
+            (p.strategy == SDCGYM_REW_ITERATION_ONLY || (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE && p.norm_init) ||
+             stream_all)) {  // (measured faster for these two; the others are FP64-latency bound, see stream_kernels.cuh)
             constexpr int sminb = SDCGYM_STREAM_MINB > 0 ? SDCGYM_STREAM_MINB : HoldPolicy<kM>::step_minb;
             constexpr size_t smem = StreamStage<kM>::bytes;
             auto kern = step_stream_kernel<kM, V, sminb>;

@@ -14,9 +14,9 @@
 // step_one<.., STEP, ..> unchanged (StepInputs points it at the stage): results are bit-identical to step_kernel.
 //
 // Measured (B200, 2^20 envs, M = 5): default reward 102 -> 93 us per step (4.2 -> 4.6 TB/s in algorithmic bytes);
-// `residual_change` 118 -> 121 us - that variant is bound by its dependent FP64 chains (ten divisions, three logarithms,
-// two norms per env: ~1000 FP64 instructions), which prefetching cannot shorten and which want the 24 warps per SM
-// that the 80-register plain kernel has.  128 registers and 2 blocks of 256 threads per SM measured best here (80
+// `residual_change` 118 -> 121 us while it re-derived the initial residual in every step, 110 -> 108 us with the
+// norm_init plane - that variant is bound by its dependent FP64 chains (ten divisions, three logarithms, a norm per
+// env), which prefetching cannot shorten.  128 registers and 2 blocks of 256 threads per SM measured best here (80
 // registers spill 200 bytes in this formulation; 128-env tiles double the number of copies and were slower).
 #pragma once
 #include "step_kernels.cuh"
