@@ -19,6 +19,7 @@
 // env), which prefetching cannot shorten.  128 registers and 2 blocks of 256 threads per SM measured best here (80
 // registers spill 200 bytes in this formulation; 128-env tiles double the number of copies and were slower).
 #pragma once
+#include "bulk_copy.cuh"
 #include "step_kernels.cuh"
 
 namespace sdcgym {
@@ -42,35 +43,12 @@ struct StreamStage {
     static constexpr int bytes = action + kStreamTile * 2 * M * 8;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done) {  // try_wait suspends the thread in hardware for a bounded time, then reports
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-// global -> shared bulk copy, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// One elected thread: arm the barrier with the tile's byte count and issue its copies.
+// Warp 0: lane 0 arms the barrier with the tile's byte count, then the lanes issue the tile's copies between them (copy
+// c by lane c % 32).  One thread issuing all 27 copies of an M = 5 tile serialises them in front of its own compute.
+#ifndef SDCGYM_STREAM_ISSUE_LANES
+#define SDCGYM_STREAM_ISSUE_LANES 32
+#endif
+constexpr int kStreamIssueLanes = SDCGYM_STREAM_ISSUE_LANES;  // (1: the single-thread issue, kept for A/B measurements)
 template <int M>
 __device__ __forceinline__ void stream_issue_tile(const StepParams<M>& p, unsigned char* stage, unsigned long long* bar,
                                                   int64_t tile, int action_row_bytes) {
@@ -78,16 +56,19 @@ __device__ __forceinline__ void stream_issue_tile(const StepParams<M>& p, unsign
     const int64_t e0 = tile * kStreamTile;
     const unsigned plane_b = kStreamTile * 8, int_b = kStreamTile * 4;
     const unsigned act_b = (unsigned)(action_row_bytes * kStreamTile);
-    mbar_expect_tx(bar, (2 + 4 * M + 1) * plane_b + 3 * int_b + act_b);
-    bulk_g2s(stage + L::lam, p.lam + e0, plane_b, bar);
-    bulk_g2s(stage + L::lam + plane_b, p.lam + p.ld + e0, plane_b, bar);
-#pragma unroll
-    for (int k = 0; k < 4 * M; k++) bulk_g2s(stage + L::S + k * plane_b, p.S + (int64_t)k * p.ld + e0, plane_b, bar);
-    bulk_g2s(stage + L::resnorm, p.resnorm + e0, plane_b, bar);
-    bulk_g2s(stage + L::niter, p.niter + e0, int_b, bar);
-    bulk_g2s(stage + L::episodes, p.episodes + e0, int_b, bar);
-    bulk_g2s(stage + L::rng_ctr, p.rng_ctr + e0, int_b, bar);
-    if (act_b) bulk_g2s(stage + L::action, p.action + e0 * p.a_es, act_b, bar);
+    const int lane = threadIdx.x;
+    if (lane == 0) mbar_expect_tx(bar, (2 + 4 * M + 1) * plane_b + 3 * int_b + act_b);
+    if (kStreamIssueLanes > 1) __syncwarp();
+    constexpr int ncopies = 2 + 4 * M + 5;
+    for (int c = lane; c < ncopies; c += kStreamIssueLanes) {
+        if (c < 2) bulk_g2s(stage + L::lam + c * plane_b, p.lam + (int64_t)c * p.ld + e0, plane_b, bar);
+        else if (c < 2 + 4 * M) bulk_g2s(stage + L::S + (c - 2) * plane_b, p.S + (int64_t)(c - 2) * p.ld + e0, plane_b, bar);
+        else if (c == 2 + 4 * M) bulk_g2s(stage + L::resnorm, p.resnorm + e0, plane_b, bar);
+        else if (c == 3 + 4 * M) bulk_g2s(stage + L::niter, p.niter + e0, int_b, bar);
+        else if (c == 4 + 4 * M) bulk_g2s(stage + L::episodes, p.episodes + e0, int_b, bar);
+        else if (c == 5 + 4 * M) bulk_g2s(stage + L::rng_ctr, p.rng_ctr + e0, int_b, bar);
+        else if (act_b) bulk_g2s(stage + L::action, p.action + e0 * p.a_es, act_b, bar);
+    }
 }
 
 // Full tiles only: the caller launches step_kernel for the tail envs [tiles * 128, N).
@@ -104,7 +85,7 @@ __global__ void __launch_bounds__(kStreamTile, MINB) step_stream_kernel(const __
     __syncthreads();
     int64_t tile = blockIdx.x;
     if (tile >= tiles) return;
-    if (threadIdx.x == 0) stream_issue_tile<M>(p, stage, &bar, tile, action_row_bytes);
+    if (threadIdx.x < kStreamIssueLanes) stream_issue_tile<M>(p, stage, &bar, tile, action_row_bytes);
     unsigned parity = 0;
     StepInputs in;
     in.lam = reinterpret_cast<const double*>(stage + L::lam);
@@ -124,7 +105,7 @@ __global__ void __launch_bounds__(kStreamTile, MINB) step_stream_kernel(const __
         // this: the stage is free again, so the next tile's copies fly while this tile is computed and stored
         auto release_and_prefetch = [&]() {
             __syncthreads();
-            if (threadIdx.x == 0 && next < tiles) stream_issue_tile<M>(p, stage, &bar, next, action_row_bytes);
+            if (threadIdx.x < kStreamIssueLanes && next < tiles) stream_issue_tile<M>(p, stage, &bar, next, action_row_bytes);
         };
         step_one<M, SDCGYM_ENV_STEP, V, false, 0>(p, tile * kStreamTile + threadIdx.x, nullptr, 1, nullptr, 1, &in,
                                                   release_and_prefetch);

@@ -8,18 +8,19 @@
 //
 // All reductions use a fixed block count and a fixed summation tree: deterministic run to run.
 #include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <math_constants.h>
 
 #include "../../include/sdcgym.h"
+#include "bulk_copy.cuh"
 #include "specrad.cuh"
 
 namespace sdcgym {
 
-#ifndef SDCGYM_ACC_BATCH
-#define SDCGYM_ACC_BATCH 8
-#endif
-constexpr int kAccBlocks = 64, kAccThreads = 256, kAccBatch = SDCGYM_ACC_BATCH;  // (the batch only groups loads: the summation order is unchanged)
+constexpr int kAccThreads = 256;
 
 __device__ __forceinline__ double2 block_sum2(double a, double b) {
     __shared__ double sa[kAccThreads / 32], sb[kAccThreads / 32];
@@ -65,43 +66,6 @@ __device__ __forceinline__ void rms_merge_one(double n, double batch, double sa,
     var = __ddiv_rn(m2, tot);
 }
 
-// partial[(p*kAccBlocks + b)*2 + {0,1}] = sum over this block's strided slice of (x - shift_p), (x - shift_p)^2
-__global__ void __launch_bounds__(kAccThreads) acc_partial_kernel(int64_t N, int64_t ld, const double* __restrict__ X,
-                                                                  const double* __restrict__ shift,
-                                                                  double* __restrict__ partial) {
-    const int p = blockIdx.y;
-    const double s = shift ? shift[p] : 0.0;
-    const double* x = X + (int64_t)p * ld;
-    double a = 0.0, b = 0.0;
-    // kAccBatch independent loads in flight per thread, accumulated in index order (the summation tree is unchanged)
-    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
-    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
-    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
-        double v[kAccBatch];
-#pragma unroll
-        for (int k = 0; k < kAccBatch; k++) v[k] = x[i + k * stride];
-#pragma unroll
-        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
-    }
-    for (; i < N; i += stride) acc_one(x[i], s, a, b);
-    double2 r = block_sum2(a, b);
-    if (threadIdx.x == 0) {
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
-    }
-}
-__global__ void acc_final_kernel(int P, const double* __restrict__ partial, double* __restrict__ out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < kAccBlocks; k++) {
-        a += partial[((int64_t)p * kAccBlocks + k) * 2];
-        b += partial[((int64_t)p * kAccBlocks + k) * 2 + 1];
-    }
-    out[p] = a;
-    out[P + p] = b;
-}
-
 // RunningMeanStd.update_from_moments with the batch given as shifted sums (shift = the running mean itself)
 __global__ void rms_merge_kernel(int P, double batch_count, const double* __restrict__ sums, double* __restrict__ mean,
                                  double* __restrict__ var, double* __restrict__ count) {
@@ -119,8 +83,8 @@ __global__ void rms_merge_kernel(int P, double batch_count, const double* __rest
 __global__ void rms_commit_kernel(double* __restrict__ count) { count[0] = count[1]; }
 
 // ---- single-rank fast path: accumulate + fold + merge in ONE launch ----------------------------------------------
-// Same partial sums as acc_partial_kernel (same slices, same tree), then the block that finishes last folds the
-// kAccBlocks partials of every plane in index order and applies the merge - bit-identical to the three-kernel
+// Same partial sums as acc_partial_kernel (stat_accumulate: same slices, same tree), then the block that finishes last
+// folds the kStatBlocks partials of every plane in index order and applies the merge - bit-identical to the three-kernel
 // sequence accumulate -> merge -> commit, without the three launches (a normalised sdc-v1 step of 2^20 envs is a
 // 115 us kernel: five 2-7 us launches per statistic were a fifth of the step).
 // RETURNS: the plane is the discounted return, advanced in the same pass: ret <- ret * gamma + reward.
@@ -157,76 +121,310 @@ __device__ __forceinline__ bool xchg_wait(volatile unsigned long long* flag, uns
     return true;
 }
 
-template <bool RETURNS, bool DIST>
-__global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
-                                                             const double* __restrict__ reward, double gamma,
-                                                             double* __restrict__ ret, double* mean, double* var,
-                                                             double* count, double* __restrict__ partial,
-                                                             double* __restrict__ sums, unsigned int* ticket,
-                                                             const XchgDev xc) {
-    const int p = blockIdx.y;
-    const double s = mean[p];
-    double a = 0.0, b = 0.0;
-    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
-    auto fetch = [&](int64_t i) {
-        if (RETURNS) {
-            const double x = advance_return(ret[i], gamma, reward[i]);
-            ret[i] = x;
-            return x;
+// ---- the statistics pass -----------------------------------------------------------------------------------------
+// One env per thread, planes in the inner loop: thread t of block b visits envs b*256 + t + k*(296*256) and, for each,
+// kStatGroup planes at a time - the access pattern that streams the plane layout at the copy peak
+// (tools/plane_stream_bench.cu: 21 planes in, 6.2-6.9 TB/s; the previous plane-per-block-row grid of 64 x P short-lived
+// blocks reached 3.6).  296 blocks of 256 threads = exactly one resident wave (2 per SM) whatever the plane count; a
+// block walks its envs once per plane group.  Plane index `nobs` (when `has_ret`) is the discounted return, advanced
+// in the same pass: ret <- ret * gamma + reward.
+// Fixed grid, fixed per-thread order, fixed block tree, partials folded in block order: deterministic, and the same
+// bits from every kernel that calls stat_accumulate (the three-kernel sequence, the fused update, the in-kernel exchange).
+#ifndef SDCGYM_STAT_UNROLL
+#define SDCGYM_STAT_UNROLL 2
+#endif
+#ifndef SDCGYM_STAT_GROUP
+#define SDCGYM_STAT_GROUP 7
+#endif
+constexpr int kStatBlocks = 296, kStatGroup = SDCGYM_STAT_GROUP, kStatUnroll = SDCGYM_STAT_UNROLL;
+
+struct StatIn {
+    int nobs, has_ret;        // observation planes X[nobs][ld]; optional return plane
+    int64_t N, ld;
+    const double* X;
+    const double* shift_obs;  // [nobs] or nullptr (no shift)
+    const double* reward;     // return plane: ret <- ret * gamma + reward
+    double gamma;
+    double* ret;
+    const double* shift_ret;  // [1] or nullptr
+};
+
+// partial[(q * kStatBlocks + blockIdx.x) * 2 + {0, 1}] for every plane q: the block walks its envs once per group of
+// kStatGroup planes (different planes each time: nothing is read twice)
+__device__ __forceinline__ void stat_accumulate(const StatIn& in, double* __restrict__ partial) {
+    const int planes = in.nobs + in.has_ret;
+    constexpr int64_t stride = (int64_t)kStatBlocks * kAccThreads;
+    for (int q0 = 0; q0 < planes; q0 += kStatGroup) {
+        double a[kStatGroup], b[kStatGroup], s[kStatGroup];
+#pragma unroll
+        for (int j = 0; j < kStatGroup; j++) {
+            a[j] = 0.0;
+            b[j] = 0.0;
+            const int q = q0 + j;
+            s[j] = 0.0;
+            if (q < in.nobs) s[j] = in.shift_obs ? in.shift_obs[q] : 0.0;
+            else if (q < planes) s[j] = in.shift_ret ? in.shift_ret[0] : 0.0;
         }
-        return X[(int64_t)p * ld + i];
-    };
-    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
-    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
-        double v[kAccBatch];
+        auto fetch = [&](int j, int64_t i) {
+            const int q = q0 + j;
+            if (q < in.nobs) return in.X[(int64_t)q * in.ld + i];
+            if (q < planes) {
+                const double x = advance_return(in.ret[i], in.gamma, in.reward[i]);
+                in.ret[i] = x;
+                return x;
+            }
+            return 0.0;
+        };
+        // kStatUnroll envs x kStatGroup planes of loads in flight per thread (predicated past the end: a separate
+        // one-env-at-a-time tail loop would spend up to kStatUnroll - 1 extra DRAM round trips at a fraction of the
+        // parallelism); the accumulation itself stays in env order, so the unrolling does not change a single bit
+        for (int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x; i < in.N; i += kStatUnroll * stride) {
+            double v[kStatUnroll][kStatGroup];
 #pragma unroll
-        for (int k = 0; k < kAccBatch; k++) v[k] = fetch(i + k * stride);
+            for (int k = 0; k < kStatUnroll; k++)
 #pragma unroll
-        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
+                for (int j = 0; j < kStatGroup; j++)
+                    v[k][j] = (i + k * stride < in.N) ? fetch(j, i + k * stride) : 0.0;
+#pragma unroll
+            for (int k = 0; k < kStatUnroll; k++)
+#pragma unroll
+                for (int j = 0; j < kStatGroup; j++)
+                    if (q0 + j < planes && i + k * stride < in.N) acc_one(v[k][j], s[j], a[j], b[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kStatGroup; j++) {
+            const int q = q0 + j;
+            if (q < planes) {  // (block-uniform)
+                const double2 r = block_sum2(a[j], b[j]);
+                if (threadIdx.x == 0) {
+                    partial[((int64_t)q * kStatBlocks + blockIdx.x) * 2] = r.x;
+                    partial[((int64_t)q * kStatBlocks + blockIdx.x) * 2 + 1] = r.y;
+                }
+            }
+        }
     }
-    for (; i < N; i += stride) acc_one(fetch(i), s, a, b);
-    double2 r = block_sum2(a, b);
+}
+// ---- the same pass with the planes arriving by bulk asynchronous copies -------------------------------------------
+// stat_accumulate issues its loads and then waits a DRAM round trip once per kStatUnroll envs: ~24 exposed round trips
+// per block at 2^20 envs (57 us for 176 MB = 3.3 TB/s).  Here a block owns the same envs in the same order (tile k of
+// block b = envs (b + 296 k) * 256 ...: thread t still sees b*256 + t + k*296*256), but the tiles of kStreamGroup
+// planes x 256 envs (2 KB per plane) are fetched by cp.async.bulk into a ring of kStreamDepth shared-memory stages,
+// completion on one mbarrier per stage; thread 0 re-arms a stage as soon as every thread has pulled its element out of
+// it.  Same per-thread order, same block tree, same partial layout: bit-identical to stat_accumulate (tested), which
+// still serves small batches, unaligned plane strides and the ragged last tile.
+#ifndef SDCGYM_STAT_STREAM_GROUP
+#define SDCGYM_STAT_STREAM_GROUP 11
+#endif
+#ifndef SDCGYM_STAT_STREAM_DEPTH
+#define SDCGYM_STAT_STREAM_DEPTH 3
+#endif
+constexpr int kStreamGroup = SDCGYM_STAT_STREAM_GROUP, kStreamDepth = SDCGYM_STAT_STREAM_DEPTH;
+constexpr int kStatTile = kAccThreads;                                  // envs per tile
+constexpr int kStatStageBytes = (kStreamGroup + 1) * kStatTile * 8;     // (+1: the reward plane next to the return plane)
+constexpr int kStatStreamSmem = kStreamDepth * kStatStageBytes;
+
+__device__ __forceinline__ void stat_accumulate_stream(const StatIn& in, double* __restrict__ partial, unsigned char* ring,
+                                                       unsigned long long* bars) {
+    const int planes = in.nobs + in.has_ret;
+    const int groups = (planes + kStreamGroup - 1) / kStreamGroup;
+    const int64_t tiles = in.N / kStatTile;  // full tiles; the ragged rest is read directly by the block that owns it
+    const int64_t mine = tiles > blockIdx.x ? (tiles - blockIdx.x + kStatBlocks - 1) / kStatBlocks : 0;
+    const int64_t total = mine * groups;
+    const int64_t tail_i = tiles * kStatTile + threadIdx.x;
+    const bool own_tail = (tiles % kStatBlocks) == blockIdx.x && tail_i < in.N;
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < kStreamDepth; d++) mbar_init(&bars[d], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // warp 0: lane 0 arms stage n % depth, then lane j issues the copy of plane j of sequence element n = (group, k-th
+    // own tile) - one thread issuing all the copies of a stage serialises them (measured: see profiles/README.md)
+    auto issue = [&](int64_t n) {
+        const int lane = threadIdx.x;
+        const int g = (int)(n / mine);
+        const int64_t e0 = (blockIdx.x + (n % mine) * kStatBlocks) * kStatTile;
+        const int st = (int)(n % kStreamDepth), q0 = g * kStreamGroup;
+        const int cnt = min(kStreamGroup, planes - q0);
+        const bool with_ret = in.has_ret && q0 + cnt == planes;
+        unsigned char* stage = ring + (size_t)st * kStatStageBytes;
+        if (lane == 0) mbar_expect_tx(&bars[st], (unsigned)((cnt + (with_ret ? 1 : 0)) * kStatTile * 8));
+        __syncwarp();
+        if (lane < cnt) {
+            const int q = q0 + lane;
+            const double* src = (q < in.nobs) ? in.X + (int64_t)q * in.ld + e0 : in.ret + e0;
+            bulk_g2s(stage + lane * kStatTile * 8, src, kStatTile * 8, &bars[st]);
+        } else if (lane == kStreamGroup && with_ret) {
+            bulk_g2s(stage + kStreamGroup * kStatTile * 8, in.reward + e0, kStatTile * 8, &bars[st]);
+        }
+    };
+    static_assert(kStreamGroup < 32, "one lane of warp 0 per plane of a stage");
+    if (threadIdx.x < 32)
+        for (int64_t n = 0; n < kStreamDepth && n < total; n++) issue(n);
+    int64_t n = 0;
+    for (int g = 0; g < groups; g++) {
+        const int q0 = g * kStreamGroup;
+        double a[kStreamGroup], b[kStreamGroup], s[kStreamGroup];
+#pragma unroll
+        for (int j = 0; j < kStreamGroup; j++) {
+            a[j] = 0.0;
+            b[j] = 0.0;
+            const int q = q0 + j;
+            s[j] = 0.0;
+            if (q < in.nobs) s[j] = in.shift_obs ? in.shift_obs[q] : 0.0;
+            else if (q < planes) s[j] = in.shift_ret ? in.shift_ret[0] : 0.0;
+        }
+        const int jret = (in.has_ret && planes - 1 >= q0 && planes - 1 < q0 + kStreamGroup) ? planes - 1 - q0 : -1;
+        for (int64_t k = 0; k < mine; k++, n++) {
+            const int st = (int)(n % kStreamDepth);
+            mbar_wait(&bars[st], (unsigned)((n / kStreamDepth) & 1));
+            const double* stage = reinterpret_cast<const double*>(ring + (size_t)st * kStatStageBytes);
+            double v[kStreamGroup + 1];
+#pragma unroll
+            for (int j = 0; j <= kStreamGroup; j++) v[j] = stage[j * kStatTile + threadIdx.x];
+            __syncthreads();  // everybody has its element: the stage is free
+            if (threadIdx.x < 32 && n + kStreamDepth < total) issue(n + kStreamDepth);
+#pragma unroll
+            for (int j = 0; j < kStreamGroup; j++) {
+                if (q0 + j < planes) {
+                    double x = v[j];
+                    if (j == jret) {
+                        x = advance_return(x, in.gamma, v[kStreamGroup]);
+                        in.ret[(blockIdx.x + k * kStatBlocks) * kStatTile + threadIdx.x] = x;
+                    }
+                    acc_one(x, s[j], a[j], b[j]);
+                }
+            }
+        }
+        if (own_tail) {
+#pragma unroll
+            for (int j = 0; j < kStreamGroup; j++) {
+                const int q = q0 + j;
+                if (q < in.nobs) acc_one(in.X[(int64_t)q * in.ld + tail_i], s[j], a[j], b[j]);
+                else if (q < planes) {
+                    const double x = advance_return(in.ret[tail_i], in.gamma, in.reward[tail_i]);
+                    in.ret[tail_i] = x;
+                    acc_one(x, s[j], a[j], b[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kStreamGroup; j++) {
+            const int q = q0 + j;
+            if (q < planes) {  // (block-uniform)
+                const double2 r = block_sum2(a[j], b[j]);
+                if (threadIdx.x == 0) {
+                    partial[((int64_t)q * kStatBlocks + blockIdx.x) * 2] = r.x;
+                    partial[((int64_t)q * kStatBlocks + blockIdx.x) * 2 + 1] = r.y;
+                }
+            }
+        }
+    }
+}
+
+// Fold the kStatBlocks partials of plane q: one warp per plane, lane l adds partials l, l + 32, ... in that order (all
+// loads of a lane in flight together), then a fixed butterfly over the lanes.  (A single thread walking the 148
+// partials is a chain of L2 round trips: 21 such threads were 40 us of a 55 us kernel.)  Every lane returns the sums.
+__device__ __forceinline__ void stat_fold(const double* __restrict__ partial, int q, double& sa, double& sb) {
+    const int lane = threadIdx.x & 31;
+    constexpr int kPer = (kStatBlocks + 31) / 32;
+    double va[kPer], vb[kPer];
+#pragma unroll
+    for (int r = 0; r < kPer; r++) {
+        const int k = lane + 32 * r;
+        va[r] = (k < kStatBlocks) ? __ldcg(&partial[((int64_t)q * kStatBlocks + k) * 2]) : 0.0;
+        vb[r] = (k < kStatBlocks) ? __ldcg(&partial[((int64_t)q * kStatBlocks + k) * 2 + 1]) : 0.0;
+    }
+    sa = 0.0;
+    sb = 0.0;
+#pragma unroll
+    for (int r = 0; r < kPer; r++) {
+        sa += va[r];
+        sb += vb[r];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+}
+
+// the three-kernel sequence: partial sums, then the fold
+template <bool STREAM>
+__global__ void __launch_bounds__(kAccThreads, 2) acc_partial_kernel(const StatIn in, double* __restrict__ partial) {
+    if constexpr (STREAM) {
+        extern __shared__ __align__(128) unsigned char ring[];
+        __shared__ __align__(8) unsigned long long bars[kStreamDepth];
+        stat_accumulate_stream(in, partial, ring, bars);
+    } else {
+        stat_accumulate(in, partial);
+    }
+}
+__global__ void __launch_bounds__(kAccThreads) acc_final_kernel(int P, const double* __restrict__ partial, double* __restrict__ out) {
+    for (int p = threadIdx.x >> 5; p < P; p += kAccThreads / 32) {  // one warp per plane
+        double a, b;
+        stat_fold(partial, p, a, b);
+        if ((threadIdx.x & 31) == 0) {
+            out[p] = a;
+            out[P + p] = b;
+        }
+    }
+}
+
+struct StatOut {
+    double *omean, *ovar, *ocount, *osums;  // observation statistics (nobs planes), sums [2 nobs (+1)]
+    double *rmean, *rvar, *rcount, *rsums;  // return statistics
+};
+
+// accumulate + fold + merge in ONE launch; DIST: with the all-reduce over peer memory in between (see above)
+template <bool DIST, bool STREAM>
+__global__ void __launch_bounds__(kAccThreads, 2) stat_update_kernel(const StatIn in, const StatOut out, double* __restrict__ partial,
+                                                                  unsigned int* ticket, const XchgDev xc) {
+    if constexpr (STREAM) {
+        extern __shared__ __align__(128) unsigned char ring[];
+        __shared__ __align__(8) unsigned long long bars[kStreamDepth];
+        stat_accumulate_stream(in, partial, ring, bars);
+    } else {
+        stat_accumulate(in, partial);
+    }
     __shared__ bool last;
     if (threadIdx.x == 0) {
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
         __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x * gridDim.y - 1);
+        last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const double n = count[0];
-    double batch = (double)N;
+    const int nobs = in.nobs, PP = in.nobs + in.has_ret;
+    const double on = nobs ? out.ocount[0] : 0.0, rn = in.has_ret ? out.rcount[0] : 0.0;
+    double batch = (double)in.N;
+    __shared__ double fa[4 * SDCGYM_MAX_M + 1], fb[4 * SDCGYM_MAX_M + 1];
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    for (int q = threadIdx.x >> 5; q < PP; q += kAccThreads / 32) {  // one warp per plane
+        double sa, sb;
+        stat_fold(partial, q, sa, sb);
+        if ((threadIdx.x & 31) == 0) {
+            fa[q] = sa;
+            fb[q] = sb;
+        }
+    }
     __syncthreads();
     if (DIST) {
-        // ---- fold the local partials, publish them to every rank, wait for everybody's ----
         const int parity = (int)(xc.seq & 1ull);
-        for (int q = threadIdx.x; q < P; q += kAccThreads) {
-            double sa = 0.0, sb = 0.0;
-            for (int k = 0; k < kAccBlocks; k++) {
-                sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
-                sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
+        for (int q = threadIdx.x; q < PP; q += kAccThreads)
+            for (int rk = 0; rk < xc.world; rk++) {
+                double* slot = xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank);
+                slot[q] = fa[q];
+                slot[PP + q] = fb[q];
             }
-            for (int r = 0; r < xc.world; r++) {
-                double* slot = xchg_slot(xc.peer[r], xc.world, xc.stride, parity, xc.rank);
-                slot[q] = sa;
-                slot[P + q] = sb;
-            }
-        }
         if (threadIdx.x == 0)
-            for (int r = 0; r < xc.world; r++) xchg_slot(xc.peer[r], xc.world, xc.stride, parity, xc.rank)[2 * P] = batch;
+            for (int rk = 0; rk < xc.world; rk++) xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank)[2 * PP] = batch;
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x < xc.world) {
             volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
             *remote = xc.seq;
-        }
-        __shared__ int timed_out;
-        if (threadIdx.x == 0) timed_out = 0;
-        __syncthreads();
-        if (threadIdx.x < xc.world) {
             volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
             if (!xchg_wait(mine, xc.seq)) timed_out = 1;
         }
@@ -234,44 +432,49 @@ __global__ void __launch_bounds__(kAccThreads) update_kernel(int P, int64_t N, i
         __syncthreads();
         double* region = xc.peer[xc.rank];
         batch = timed_out ? CUDART_NAN : 0.0;
-        for (int r = 0; r < xc.world; r++)
-            batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, r) + 2 * P);
-        for (int q = threadIdx.x; q < P; q += kAccThreads) {
+        for (int rk = 0; rk < xc.world; rk++) batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, rk) + 2 * PP);
+        for (int q = threadIdx.x; q < PP; q += kAccThreads) {
             double sa = 0.0, sb = 0.0;
-            for (int r = 0; r < xc.world; r++) {
-                const double* slot = xchg_slot(region, xc.world, xc.stride, parity, r);
+            for (int rk = 0; rk < xc.world; rk++) {
+                const double* slot = xchg_slot(region, xc.world, xc.stride, parity, rk);
                 sa += __ldcv(slot + q);
-                sb += __ldcv(slot + P + q);
+                sb += __ldcv(slot + PP + q);
             }
-            sums[q] = sa;
-            sums[P + q] = sb;
-            double m = mean[q], v = var[q];
-            if (batch > 0.0 || batch != batch) rms_merge_one(n, batch, sa, sb, m, v);  // (NaN batch: a peer timed out)
-            mean[q] = m;
-            var[q] = v;
+            fa[q] = sa;
+            fb[q] = sb;
         }
-    } else {
-        for (int q = threadIdx.x; q < P; q += kAccThreads) {
-            double sa = 0.0, sb = 0.0;
-            for (int k = 0; k < kAccBlocks; k++) {
-                sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
-                sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
-            }
-            sums[q] = sa;
-            sums[P + q] = sb;
-            double m = mean[q], v = var[q];
-            rms_merge_one(n, batch, sa, sb, m, v);
-            mean[q] = m;
-            var[q] = v;
+        __syncthreads();
+    }
+    const bool merge = (batch > 0.0) || (batch != batch);  // (NaN batch: a peer timed out - poison the statistics)
+    for (int q = threadIdx.x; q < PP; q += kAccThreads) {
+        if (q < nobs) {
+            out.osums[q] = fa[q];
+            out.osums[nobs + q] = fb[q];
+            double m = out.omean[q], v = out.ovar[q];
+            if (merge) rms_merge_one(on, batch, fa[q], fb[q], m, v);
+            out.omean[q] = m;
+            out.ovar[q] = v;
+        } else {
+            out.rsums[0] = fa[q];
+            out.rsums[1] = fb[q];
+            double m = out.rmean[0], v = out.rvar[0];
+            if (merge) rms_merge_one(rn, batch, fa[q], fb[q], m, v);
+            out.rmean[0] = m;
+            out.rvar[0] = v;
         }
     }
     if (threadIdx.x == 0) {
-        count[0] = n + batch;
-        count[1] = n + batch;
+        if (nobs) {
+            out.ocount[0] = on + batch;
+            out.ocount[1] = on + batch;
+        }
+        if (in.has_ret) {
+            out.rcount[0] = rn + batch;
+            out.rcount[1] = rn + batch;
+        }
         *ticket = 0u;  // self-cleaning: ready for the next launch on this stream
     }
 }
-
 
 __global__ void apply_kernel(int64_t N, int64_t ld, const double* __restrict__ X, const double* __restrict__ mean,
                              const double* __restrict__ var, double eps, double clip, double* __restrict__ Y) {
@@ -483,156 +686,6 @@ extern "C" int sdcgym_gae(int T, int64_t N, const double* rewards, const double*
     return (int)cudaGetLastError();
 }
 
-extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kAccBlocks * 2 + 2; }  // partials + the ticket word
-
-// ---- observation planes AND the return plane in one launch (grid.y = P + 1; plane P is the discounted return, advanced
-//      in the same pass).  Same slices, same trees, same merges as the two separate launches - bit-identical results -
-//      but one launch, one ticket and, with several ranks, ONE exchange for both statistics; the 64 blocks of the
-//      return plane no longer have the GPU to themselves. ----
-template <bool DIST>
-__global__ void __launch_bounds__(kAccThreads) update_both_kernel(int P, int64_t N, int64_t ld, const double* __restrict__ X,
-                                                                  const double* __restrict__ reward, double gamma,
-                                                                  double* __restrict__ ret, double* omean, double* ovar,
-                                                                  double* ocount, double* rmean, double* rvar,
-                                                                  double* rcount, double* __restrict__ partial,
-                                                                  double* __restrict__ osums, double* __restrict__ rsums,
-                                                                  unsigned int* ticket, const XchgDev xc) {
-    const int p = blockIdx.y;
-    const bool is_ret = (p == P);
-    const double s = is_ret ? rmean[0] : omean[p];
-    double a = 0.0, b = 0.0;
-    constexpr int64_t stride = (int64_t)kAccBlocks * kAccThreads;
-    auto fetch = [&](int64_t i) {
-        if (is_ret) {
-            const double x = advance_return(ret[i], gamma, reward[i]);
-            ret[i] = x;
-            return x;
-        }
-        return X[(int64_t)p * ld + i];
-    };
-    int64_t i = (int64_t)blockIdx.x * kAccThreads + threadIdx.x;
-    for (; i + (kAccBatch - 1) * stride < N; i += kAccBatch * stride) {
-        double v[kAccBatch];
-#pragma unroll
-        for (int k = 0; k < kAccBatch; k++) v[k] = fetch(i + k * stride);
-#pragma unroll
-        for (int k = 0; k < kAccBatch; k++) acc_one(v[k], s, a, b);
-    }
-    for (; i < N; i += stride) acc_one(fetch(i), s, a, b);
-    double2 r = block_sum2(a, b);
-    __shared__ bool last;
-    if (threadIdx.x == 0) {
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2] = r.x;
-        partial[((int64_t)p * kAccBlocks + blockIdx.x) * 2 + 1] = r.y;
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x * gridDim.y - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const double on = ocount[0], rn = rcount[0];
-    double batch = (double)N;
-    const int PP = P + 1;
-    __shared__ double fa[4 * SDCGYM_MAX_M + 1], fb[4 * SDCGYM_MAX_M + 1];
-    __syncthreads();
-    for (int q = threadIdx.x; q < PP; q += kAccThreads) {
-        double sa = 0.0, sb = 0.0;
-        for (int k = 0; k < kAccBlocks; k++) {
-            sa += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2]);
-            sb += __ldcg(&partial[((int64_t)q * kAccBlocks + k) * 2 + 1]);
-        }
-        fa[q] = sa;
-        fb[q] = sb;
-    }
-    __syncthreads();
-    if (DIST) {
-        const int parity = (int)(xc.seq & 1ull);
-        for (int q = threadIdx.x; q < PP; q += kAccThreads)
-            for (int rk = 0; rk < xc.world; rk++) {
-                double* slot = xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank);
-                slot[q] = fa[q];
-                slot[PP + q] = fb[q];
-            }
-        if (threadIdx.x == 0)
-            for (int rk = 0; rk < xc.world; rk++) xchg_slot(xc.peer[rk], xc.world, xc.stride, parity, xc.rank)[2 * PP] = batch;
-        __threadfence_system();
-        __syncthreads();
-        __shared__ int timed_out;
-        if (threadIdx.x == 0) timed_out = 0;
-        __syncthreads();
-        if (threadIdx.x < xc.world) {
-            volatile unsigned long long* remote = xchg_flags(xc.peer[threadIdx.x], xc.world, xc.stride, parity) + xc.rank;
-            *remote = xc.seq;
-            volatile unsigned long long* mine = xchg_flags(xc.peer[xc.rank], xc.world, xc.stride, parity) + threadIdx.x;
-            if (!xchg_wait(mine, xc.seq)) timed_out = 1;
-        }
-        __threadfence_system();
-        __syncthreads();
-        double* region = xc.peer[xc.rank];
-        batch = timed_out ? CUDART_NAN : 0.0;
-        for (int rk = 0; rk < xc.world; rk++) batch += __ldcv(xchg_slot(region, xc.world, xc.stride, parity, rk) + 2 * PP);
-        for (int q = threadIdx.x; q < PP; q += kAccThreads) {
-            double sa = 0.0, sb = 0.0;
-            for (int rk = 0; rk < xc.world; rk++) {
-                const double* slot = xchg_slot(region, xc.world, xc.stride, parity, rk);
-                sa += __ldcv(slot + q);
-                sb += __ldcv(slot + PP + q);
-            }
-            fa[q] = sa;
-            fb[q] = sb;
-        }
-        __syncthreads();
-    }
-    for (int q = threadIdx.x; q < PP; q += kAccThreads) {
-        if (q < P) {
-            osums[q] = fa[q];
-            osums[P + q] = fb[q];
-            double m = omean[q], v = ovar[q];
-            if (batch > 0.0 || batch != batch) rms_merge_one(on, batch, fa[q], fb[q], m, v);  // (NaN: a peer timed out)
-            omean[q] = m;
-            ovar[q] = v;
-        } else {
-            rsums[0] = fa[q];
-            rsums[1] = fb[q];
-            double m = rmean[0], v = rvar[0];
-            if (batch > 0.0 || batch != batch) rms_merge_one(rn, batch, fa[q], fb[q], m, v);
-            rmean[0] = m;
-            rvar[0] = v;
-        }
-    }
-    if (threadIdx.x == 0) {
-        ocount[0] = on + batch;
-        ocount[1] = on + batch;
-        rcount[0] = rn + batch;
-        rcount[1] = rn + batch;
-        *ticket = 0u;
-    }
-}
-
-extern "C" int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
-                                     double* count2, double* scratch, double* sums, void* stream) {
-    if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
-    if (N == 0) return 0;
-    if (!X || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)P * kAccBlocks * 2);
-    update_kernel<false, false><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
-        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket, XchgDev{});
-    return (int)cudaGetLastError();
-}
-
-extern "C" int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, double gamma, double* returns, double* mean,
-                                             double* var, double* count2, double* scratch, double* sums, void* stream) {
-    if (N < 0) return SDCGYM_EINVAL;
-    if (N == 0) return 0;
-    if (!reward || !returns || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
-    update_kernel<true, false><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
-        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket, XchgDev{});
-    return (int)cudaGetLastError();
-}
-
-// ---- multi-rank: the same single launch with the all-reduce of the moment sums over peer memory ------------------
 static int fill_xchg(const sdcgym_xchg* x, int P, XchgDev& d) {
     if (!x) return SDCGYM_ENULL;
     if (x->world < 1 || x->world > SDCGYM_MAX_RANKS || x->rank < 0 || x->rank >= x->world) return SDCGYM_EINVAL;
@@ -653,58 +706,118 @@ extern "C" size_t sdcgym_xchg_bytes(int world, int slot_doubles) {
     return ((size_t)2 * world * slot_doubles) * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
 }
 
+extern "C" int sdcgym_vecnorm_scratch_doubles(int P) { return P * kStatBlocks * 2 + 2; }  // partials + the ticket word
+
+// the bulk-copy variant needs full tiles for every block and 16-byte aligned plane rows
+static bool stat_stream_ok(const StatIn& in) {
+    const bool off = getenv("SDCGYM_NO_STAT_STREAM") != nullptr;  // A/B switch (read per call: the parity test toggles it)
+    if (off || in.N < (int64_t)kStatBlocks * kStatTile) return false;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (in.nobs && (!al(in.X) || (in.ld & 1))) return false;
+    if (in.has_ret && (!al(in.ret) || !al(in.reward))) return false;
+    return true;
+}
+// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+template <class K>
+static cudaError_t stat_smem_attr(K kernel) {
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = (dev >= 0 && dev < 64) ? (uint64_t(1) << dev) : 0;
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStatStreamSmem);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
+}
+
+// one launch for any combination of observation planes and return plane, single rank or in-kernel exchange
+static int launch_stat_update(int nobs, int64_t N, int64_t ld, const double* X, const double* reward, double gamma,
+                              double* returns, bool has_ret, double* omean, double* ovar, double* ocount, double* osums,
+                              double* rmean, double* rvar, double* rcount, double* rsums, double* scratch,
+                              const sdcgym_xchg* xchg, void* stream) {
+    const int PP = nobs + (has_ret ? 1 : 0);
+    if (PP < 1 || nobs > 4 * SDCGYM_MAX_M || N < 0 || ld < N) return SDCGYM_EINVAL;
+    if (!scratch) return SDCGYM_ENULL;
+    if (nobs && ((N > 0 && !X) || !omean || !ovar || !ocount || !osums)) return SDCGYM_ENULL;
+    if (has_ret && ((N > 0 && (!reward || !returns)) || !rmean || !rvar || !rcount || !rsums)) return SDCGYM_ENULL;
+    if (!xchg && N == 0) return 0;  // (an empty shard still takes part in an exchange)
+    StatIn in{nobs, has_ret ? 1 : 0, N, ld, X, omean, reward, gamma, returns, rmean};
+    StatOut out{omean, ovar, ocount, osums, rmean, rvar, rcount, rsums};
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)PP * kStatBlocks * 2);
+    const dim3 grid(kStatBlocks);
+    const bool stream_ok = stat_stream_ok(in);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (xchg) {
+        XchgDev d{};
+        int rc = fill_xchg(xchg, PP, d);
+        if (rc) return rc;
+        if (stream_ok) {
+            if ((e = stat_smem_attr(stat_update_kernel<true, true>)) != cudaSuccess) return (int)e;
+            stat_update_kernel<true, true><<<grid, kAccThreads, kStatStreamSmem, s>>>(in, out, scratch, ticket, d);
+        } else {
+            stat_update_kernel<true, false><<<grid, kAccThreads, 0, s>>>(in, out, scratch, ticket, d);
+        }
+    } else if (stream_ok) {
+        if ((e = stat_smem_attr(stat_update_kernel<false, true>)) != cudaSuccess) return (int)e;
+        stat_update_kernel<false, true><<<grid, kAccThreads, kStatStreamSmem, s>>>(in, out, scratch, ticket, XchgDev{});
+    } else {
+        stat_update_kernel<false, false><<<grid, kAccThreads, 0, s>>>(in, out, scratch, ticket, XchgDev{});
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sdcgym_vecnorm_update(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
+                                     double* count2, double* scratch, double* sums, void* stream) {
+    if (P < 1) return SDCGYM_EINVAL;
+    return launch_stat_update(P, N, ld, X, nullptr, 0.0, nullptr, false, mean, var, count2, sums, nullptr, nullptr, nullptr,
+                              nullptr, scratch, nullptr, stream);
+}
+extern "C" int sdcgym_vecnorm_update_returns(int64_t N, const double* reward, double gamma, double* returns, double* mean,
+                                             double* var, double* count2, double* scratch, double* sums, void* stream) {
+    return launch_stat_update(0, N, N, nullptr, reward, gamma, returns, true, nullptr, nullptr, nullptr, nullptr, mean, var,
+                              count2, sums, scratch, nullptr, stream);
+}
 extern "C" int sdcgym_vecnorm_update_dist(int P, int64_t N, int64_t ld, const double* X, double* mean, double* var,
                                           double* count2, double* scratch, double* sums, const sdcgym_xchg* xchg,
                                           void* stream) {
-    if (P < 1 || P > kAccThreads * 4 || N < 0 || ld < N) return SDCGYM_EINVAL;
-    if ((N > 0 && !X) || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
-    XchgDev d{};
-    int rc = fill_xchg(xchg, P, d);
-    if (rc) return rc;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)P * kAccBlocks * 2);
-    // (an empty shard still takes part in the exchange)
-    update_kernel<false, true><<<dim3(kAccBlocks, P), kAccThreads, 0, (cudaStream_t)stream>>>(
-        P, N, ld, X, nullptr, 0.0, nullptr, mean, var, count2, scratch, sums, ticket, d);
-    return (int)cudaGetLastError();
+    if (P < 1 || !xchg) return xchg ? SDCGYM_EINVAL : SDCGYM_ENULL;
+    return launch_stat_update(P, N, ld, X, nullptr, 0.0, nullptr, false, mean, var, count2, sums, nullptr, nullptr, nullptr,
+                              nullptr, scratch, xchg, stream);
 }
-
 extern "C" int sdcgym_vecnorm_update_returns_dist(int64_t N, const double* reward, double gamma, double* returns,
                                                   double* mean, double* var, double* count2, double* scratch,
                                                   double* sums, const sdcgym_xchg* xchg, void* stream) {
-    if (N < 0) return SDCGYM_EINVAL;
-    if ((N > 0 && (!reward || !returns)) || !mean || !var || !count2 || !scratch || !sums) return SDCGYM_ENULL;
-    XchgDev d{};
-    int rc = fill_xchg(xchg, 1, d);
-    if (rc) return rc;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)kAccBlocks * 2);
-    update_kernel<true, true><<<dim3(kAccBlocks, 1), kAccThreads, 0, (cudaStream_t)stream>>>(
-        1, N, N, nullptr, reward, gamma, returns, mean, var, count2, scratch, sums, ticket, d);
-    return (int)cudaGetLastError();
+    if (!xchg) return SDCGYM_ENULL;
+    return launch_stat_update(0, N, N, nullptr, reward, gamma, returns, true, nullptr, nullptr, nullptr, nullptr, mean, var,
+                              count2, sums, scratch, xchg, stream);
 }
-
 extern "C" int sdcgym_vecnorm_update_both(int P, int64_t N, int64_t ld, const double* X, const double* reward, double gamma,
                                           double* returns, double* obs_mean, double* obs_var, double* obs_count2,
                                           double* ret_mean, double* ret_var, double* ret_count2, double* scratch,
                                           double* sums_obs, double* sums_ret, const sdcgym_xchg* xchg, void* stream) {
+    if (P < 1) return SDCGYM_EINVAL;
+    return launch_stat_update(P, N, ld, X, reward, gamma, returns, true, obs_mean, obs_var, obs_count2, sums_obs, ret_mean,
+                              ret_var, ret_count2, sums_ret, scratch, xchg, stream);
+}
+
+extern "C" int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift,
+                                         double* scratch, double* sums, void* stream) {
     if (P < 1 || P > 4 * SDCGYM_MAX_M || N < 0 || ld < N) return SDCGYM_EINVAL;
-    if ((N > 0 && (!X || !reward || !returns)) || !obs_mean || !obs_var || !obs_count2 || !ret_mean || !ret_var ||
-        !ret_count2 || !scratch || !sums_obs || !sums_ret)
-        return SDCGYM_ENULL;
-    if (!xchg && N == 0) return 0;
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (int64_t)(P + 1) * kAccBlocks * 2);
-    const dim3 grid(kAccBlocks, P + 1);
-    if (xchg) {
-        XchgDev d{};
-        int rc = fill_xchg(xchg, P + 1, d);
-        if (rc) return rc;
-        update_both_kernel<true><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
-            P, N, ld, X, reward, gamma, returns, obs_mean, obs_var, obs_count2, ret_mean, ret_var, ret_count2, scratch,
-            sums_obs, sums_ret, ticket, d);
+    if (!X || !scratch || !sums) return SDCGYM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    StatIn in{P, 0, N, ld, X, shift, nullptr, 0.0, nullptr, nullptr};
+    if (stat_stream_ok(in)) {
+        cudaError_t e = stat_smem_attr(acc_partial_kernel<true>);
+        if (e != cudaSuccess) return (int)e;
+        acc_partial_kernel<true><<<kStatBlocks, kAccThreads, kStatStreamSmem, s>>>(in, scratch);
     } else {
-        update_both_kernel<false><<<grid, kAccThreads, 0, (cudaStream_t)stream>>>(
-            P, N, ld, X, reward, gamma, returns, obs_mean, obs_var, obs_count2, ret_mean, ret_var, ret_count2, scratch,
-            sums_obs, sums_ret, ticket, XchgDev{});
+        acc_partial_kernel<false><<<kStatBlocks, kAccThreads, 0, s>>>(in, scratch);
     }
+    acc_final_kernel<<<1, kAccThreads, 0, s>>>(P, scratch, sums);
     return (int)cudaGetLastError();
 }
 
@@ -737,16 +850,6 @@ extern "C" int sdcgym_ipc_open(const unsigned char* handle64, void** dev_ptr) {
 }
 extern "C" int sdcgym_ipc_close(void* dev_ptr) { return dev_ptr ? (int)cudaIpcCloseMemHandle(dev_ptr) : 0; }
 extern "C" int sdcgym_ipc_free(void* dev_ptr) { return dev_ptr ? (int)cudaFree(dev_ptr) : 0; }
-
-extern "C" int sdcgym_vecnorm_accumulate(int P, int64_t N, int64_t ld, const double* X, const double* shift,
-                                         double* scratch, double* sums, void* stream) {
-    if (P < 1 || N < 0 || ld < N) return SDCGYM_EINVAL;
-    if (!X || !scratch || !sums) return SDCGYM_ENULL;
-    cudaStream_t s = (cudaStream_t)stream;
-    acc_partial_kernel<<<dim3(kAccBlocks, P), kAccThreads, 0, s>>>(N, ld, X, shift, scratch);
-    acc_final_kernel<<<(P + 63) / 64, 64, 0, s>>>(P, scratch, sums);
-    return (int)cudaGetLastError();
-}
 
 extern "C" int sdcgym_vecnorm_merge(int P, double batch_count, const double* sums, double* mean, double* var,
                                     double* count2, void* stream) {

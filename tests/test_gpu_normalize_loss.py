@@ -101,6 +101,52 @@ def test_fused_statistics_update_is_bit_identical_to_the_three_kernel_sequence()
     assert envs[0].obs_rms.count == pytest.approx(1e-4 + 21 * n)
 
 
+@pytest.mark.parametrize("M,n", [(5, 296 * 256 * 2 + 77), (9, 296 * 256 + 256 * 5), (3, 296 * 256 * 3)])
+def test_bulk_copy_statistics_pass_is_bit_identical_to_the_plain_pass(M, n):
+    """csrc/vecnorm.cu stat_accumulate_stream (planes fetched by cp.async.bulk into a shared-memory ring; large
+    batches) against stat_accumulate (direct loads; SDCGYM_NO_STAT_STREAM=1): same per-thread order, same trees -
+    every moment, every return and the three-kernel sequence must agree bit for bit (ragged last tile included)."""
+    import os
+    import torch
+
+    def same_bits(a, b):  # (uniform random actions: diverged envs carry NaN rewards, and NaN != NaN)
+        if a.dtype == torch.float64:
+            a, b = a.contiguous().view(torch.int64), b.contiguous().view(torch.int64)
+        return torch.equal(a, b)
+
+    kw = dict(KW, M=M)
+    envs = []
+    for _ in range(3):
+        e = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=n, seed=11, reward_iteration_only=False,
+                                                        output="torch", **kw), gamma=0.9)
+        envs.append(e)
+    envs[2].fused_update = False  # accumulate -> merge -> commit, streaming accumulate
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    try:
+        os.environ["SDCGYM_NO_STAT_STREAM"] = "1"
+        envs[1].reset()
+        os.environ.pop("SDCGYM_NO_STAT_STREAM")
+        envs[0].reset(); envs[2].reset()
+        for s in range(4):
+            act = torch.rand((n, M), dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+            outs = []
+            for k, e in enumerate(envs):
+                if k == 1:
+                    os.environ["SDCGYM_NO_STAT_STREAM"] = "1"
+                outs.append(e.step_tensor(act))
+                os.environ.pop("SDCGYM_NO_STAT_STREAM", None)
+            for k in (1, 2):
+                for key in ("obs_planes", "reward", "raw_reward", "flags"):
+                    assert same_bits(outs[0][key], outs[k][key]), f"step {s} {key} variant {k}"
+                for rms in ("obs_rms", "ret_rms"):
+                    a, b = getattr(envs[0], rms), getattr(envs[k], rms)
+                    assert same_bits(a.mean, b.mean) and same_bits(a.var, b.var) and same_bits(a.count2, b.count2), (s, rms, k)
+                assert same_bits(envs[0].returns, envs[k].returns)
+    finally:
+        os.environ.pop("SDCGYM_NO_STAT_STREAM", None)
+    assert envs[0].obs_rms.count == pytest.approx(1e-4 + 5 * n)
+
+
 @pytest.mark.parametrize("n", [8, 1000, 5000])
 def test_native_normalised_host_step_equals_the_call_by_call_path(n):
     """VecNormalize.step(numpy) through sdcgym_pipe_step_vecnorm (one C call; packed single transfer for small
