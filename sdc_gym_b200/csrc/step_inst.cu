@@ -66,7 +66,8 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
                                           (reinterpret_cast<uintptr_t>(p.action) & 15u) == 0);
         const bool aligned = ((reinterpret_cast<uintptr_t>(p.lam) | reinterpret_cast<uintptr_t>(p.S) |
                                reinterpret_cast<uintptr_t>(p.resnorm) | reinterpret_cast<uintptr_t>(p.niter) |
-                               reinterpret_cast<uintptr_t>(p.episodes) | reinterpret_cast<uintptr_t>(p.rng_ctr)) & 15u) == 0 &&
+                               reinterpret_cast<uintptr_t>(p.episodes) | reinterpret_cast<uintptr_t>(p.rng_ctr) |
+                               reinterpret_cast<uintptr_t>(p.norm_init)) & 15u) == 0 &&
                              (p.ld % 2) == 0;
         const int64_t tiles = p.N / kStreamTile;
         if (!no_stream && p.old_states == nullptr && rows_ok && aligned && tiles >= 148 * 2 &&

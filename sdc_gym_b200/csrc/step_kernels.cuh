@@ -363,7 +363,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     // consume everything here: keeps the loads above this point.  (Not for the dense kernels: they load the Q_delta
     // entries next and a barrier here would only add a second exposed round trip - measured 20 % slower at M = 3.)
     if (!DENSE) {
-        asm volatile("" : "+d"(lr), "+d"(li), "+d"(nr_old), "+r"(it), "+r"(ep_old), "+r"(ctr_old));
+        asm volatile("" : "+d"(lr), "+d"(li), "+d"(nr_old), "+d"(ninit_cached), "+r"(it), "+r"(ep_old), "+r"(ctr_old));
 #pragma unroll
         for (int k = 0; k < M; k++) asm volatile("" : "+d"(araw[k]), "+d"(aimg[k]));
 #pragma unroll

@@ -19,7 +19,7 @@ KW = dict(dt=1.0, restol=1e-10, lambda_real_interval=[-100, 0], lambda_imag_inte
 
 
 @pytest.mark.parametrize("M", [3, 5, 7])
-@pytest.mark.parametrize("variant", ["real", "complex", "min", "residual_change"])  # (the last one: plain kernel)
+@pytest.mark.parametrize("variant", ["real", "complex", "min", "residual_change"])  # (the last one: with the staged norm_init plane)
 def test_streaming_step_equals_oracle(M, variant):
     Q = collocation_matrix(M)
     rng = np.random.default_rng(M)
