@@ -39,6 +39,12 @@ for N in args.envs:
     with torch.cuda.device(dev):
         both = timed(lambda: vn._update_both(N))
         obs = timed(lambda: vn._update(vn.obs_rms, env.S.data_ptr(), P, N, env.ld, vn._sums))
+        r = vn.ret_rms
+        import ctypes
+        L = vn._L
+        rets = timed(lambda: L.sdcgym_vecnorm_update_returns(
+            N, env.reward.data_ptr(), vn.gamma, vn.returns.data_ptr(), r.mean.data_ptr(), r.var.data_ptr(),
+            r.count2.data_ptr(), vn._rscratch.data_ptr(), vn._rsums.data_ptr(), vn._stream()))
         vn.fused_update = False
         three = timed(lambda: vn._update(vn.obs_rms, env.S.data_ptr(), P, N, env.ld, vn._sums))
         vn.fused_update = True
@@ -47,7 +53,7 @@ for N in args.envs:
         nstep = timed(lambda: vn.step_tensor(a))
     print(json.dumps({"tag": args.tag, "envs": N, "M": M,
                       "update_both_us": both, "update_both_GBps": (P + 3) * 8 * N / both / 1e3,
-                      "update_obs_us": obs, "three_kernel_obs_us": three,
+                      "update_obs_us": obs, "update_returns_us": rets, "three_kernel_obs_us": three,
                       "apply_us": app, "apply_GBps": 2 * P * 8 * N / app / 1e3,
                       "step_us": step, "normalised_step_us": nstep}), flush=True)
     del vn, env
