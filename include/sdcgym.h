@@ -130,7 +130,8 @@ typedef struct sdcgym_state {
     double* norm_init; /* [ld] or NULL: ||initial residual of the running episode||_inf (scaled by norm_factor), written by
                         * every reset / auto-reset.  The `residual_change` reward divides by its logarithm
                         * (sdc_env.py:337-350); with the plane the step reads 8 bytes instead of re-deriving the initial
-                        * state and its norm (~250 FP64 instructions per env-step).  Same bits either way. */
+                        * state and its norm (~250 FP64 instructions per env-step).  Same bits either way.  Used by
+                        * sdc-v1 (SDCGYM_ENV_STEP) only: the sdc-v0 step kernels neither read nor refresh it. */
     /* work buffers of SDCGYM_SWEEP_CERTIFIED (NULL otherwise): */
     float* cert;            /* [SDCGYM_CERT_PLANES][ld] per-env certificate constants, rewritten by every step */
     int32_t* fallback_list; /* [N] indices of the envs the exact kernel re-ran in the last step */

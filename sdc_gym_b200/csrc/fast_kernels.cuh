@@ -307,8 +307,7 @@ SDCGYM_HD void fast_step_one(const StepParams<M>& p, const FastWork& fw, const i
         initial_state<M, V>(p.Q, nzr, nzi, ur, ui, rr, ri);
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);
         const double n0 = inf_norm_fast<M>(rr, ri);
-        p.resnorm[i] = n0;
-        store_norm_init<M>(p, i, rr, ri, n0);
+        p.resnorm[i] = n0;  // (no norm_init store: sdc-v0 kernels do not keep that plane, see step_one)
         p.niter[i] = 0;
     } else {
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);

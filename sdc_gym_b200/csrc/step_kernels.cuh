@@ -357,13 +357,18 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     uint32_t ctr_old = p.autoreset ? (in ? in->rng_ctr[ii] : p.rng_ctr[i]) : 0u;
     // cached ||initial residual|| of the episode (residual_change reward); NaN marks "not cached: re-derive"
     double ninit_cached = d_nan();
-    if (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE && p.norm_init)
+    // (sdc-v1 only: one more live value and one more store in the sdc-v0 kernel measured 2 % on the headline step, and a
+    //  full solve amortises the re-derivation over ~43 sweeps)
+    constexpr bool kUseNinit = (KIND == SDCGYM_ENV_STEP);
+    if (kUseNinit && p.strategy == SDCGYM_REW_RESIDUAL_CHANGE && p.norm_init)
         ninit_cached = (in && in->norm_init) ? in->norm_init[ii] : p.norm_init[i];
 #ifdef __CUDA_ARCH__
     // consume everything here: keeps the loads above this point.  (Not for the dense kernels: they load the Q_delta
     // entries next and a barrier here would only add a second exposed round trip - measured 20 % slower at M = 3.)
     if (!DENSE) {
-        asm volatile("" : "+d"(lr), "+d"(li), "+d"(nr_old), "+d"(ninit_cached), "+r"(it), "+r"(ep_old), "+r"(ctr_old));
+        asm volatile("" : "+d"(lr), "+d"(li), "+d"(nr_old), "+r"(it), "+r"(ep_old), "+r"(ctr_old));
+        // (ninit_cached needs no entry: the streaming kernel's release callback below starts with a block barrier,
+        //  which the compiler does not move shared-memory loads across; listing it cost the sdc-v0 kernel 2 %)
 #pragma unroll
         for (int k = 0; k < M; k++) asm volatile("" : "+d"(araw[k]), "+d"(aimg[k]));
 #pragma unroll
@@ -680,7 +685,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     } else {
         double norm_init_scaled = 0.0;
         if (p.strategy == SDCGYM_REW_RESIDUAL_CHANGE) {
-            if (p.norm_init) {
+            if (kUseNinit && p.norm_init) {
                 norm_init_scaled = ninit_cached;  // written by the reset of this episode (same function, same bits)
             } else {
                 // initial residual of the episode is a function of lambda only: recompute it
@@ -726,7 +731,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);
         const double n0 = inf_norm_fast<M>(rr, ri);
         p.resnorm[i] = n0;
-        store_norm_init<M>(p, i, rr, ri, n0);
+        if (kUseNinit) store_norm_init<M>(p, i, rr, ri, n0);
         p.niter[i] = 0;
     } else {
         store_state<M>(p.S, ld, i, ur, ui, rr, ri);

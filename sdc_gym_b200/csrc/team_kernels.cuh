@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
         __syncwarp();  // every lane has read the last residual exchange
         exchange(xr, nrr, nri, Ir, Ii);
         nres = inf_norm_fast<M>(Ir, Ii);
-        ninit = (p.norm_init && p.norm_factor != 1.0) ? scaled_inf_norm<M>(Ir, Ii, p.norm_factor) : nres;
+        ninit = (KIND == SDCGYM_ENV_STEP && p.norm_init && p.norm_factor != 1.0) ? scaled_inf_norm<M>(Ir, Ii, p.norm_factor) : nres;
     }
     if (!valid) return;
 
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kTeamBlock, MINB) team_step_kernel(const __gri
             p.lam[i] = nlr;
             p.lam[ld + i] = nli;
             p.resnorm[i] = nres;
-            if (p.norm_init) p.norm_init[i] = ninit;
+            if (KIND == SDCGYM_ENV_STEP && p.norm_init) p.norm_init[i] = ninit;
             p.niter[i] = 0;
         }
     } else {
