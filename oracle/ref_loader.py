@@ -143,3 +143,54 @@ def inject_lambda(env, lam):
         env.old_states[:, 0] = np.concatenate(env.state)
         env.old_states[:, 1:] = 0
     return env.state
+
+
+# ---- sdc-v4 (SDC_Full_Force_Env, sdc_force_env.py:7-118) --------------------------------------------------------
+_cached_force = None
+
+
+def force_reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "sdc_gym", "envs", "sdc_force_env.py")) and reference_available()
+
+
+def load_reference_force_env():
+    """The unmodified ``sdc_force_env.py`` loaded by path.  It imports its base class relatively
+    (``from .sdc_env import SDC_Full_Env``, ``sdc_force_env.py:4``), so the two files are mounted as submodules of a
+    synthetic package instead of going through ``sdc_gym/__init__.py`` (gym registry, jax)."""
+    global _cached_force
+    if _cached_force is not None:
+        return _cached_force
+    base = load_reference_envs()
+    pkg = types.ModuleType("_reference_envs_pkg")
+    pkg.__path__ = []  # a package: relative imports resolve against sys.modules
+    sys.modules["_reference_envs_pkg"] = pkg
+    sys.modules["_reference_envs_pkg.sdc_env"] = base
+    path = os.path.join(REFERENCE_ROOT, "sdc_gym", "envs", "sdc_force_env.py")
+    spec = importlib.util.spec_from_file_location("_reference_envs_pkg.sdc_force_env", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_reference_envs_pkg.sdc_force_env"] = mod
+    spec.loader.exec_module(mod)
+    _cached_force = mod
+    return mod
+
+
+def make_reference_force_env(*, lam=None, **kwargs):
+    """``SDC_Full_Force_Env`` with the ONE repair without which no non-diverging step of the reference completes:
+    ``step`` calls ``self.reward_func(initial_residual, residual, done, niter)`` (``sdc_force_env.py:77-82``) although
+    ``reward_func`` takes six positional arguments (``sdc_env.py:427-435``) - a TypeError.  The instance gets a
+    ``reward_func`` that supplies ``None`` for the two omitted arguments (``scaled_action``, ``Pinv``: read only by the
+    ``spectral_radius`` strategy, which therefore stays unusable); class, ``step`` and ``reset`` are the reference's."""
+    mod = load_reference_force_env()
+    env = mod.SDC_Full_Force_Env(**kwargs)
+    orig = env.reward_func
+    env.reward_func = lambda old, res, conv, steps, scaled_action=None, Pinv=None: orig(old, res, conv, steps,
+                                                                                        scaled_action, Pinv)
+    if lam is not None:
+        env.reset()
+        env.lam = complex(lam)
+        env._compute_system_matrix()
+        u = np.ones(env.M, dtype=np.complex128)
+        residual = env._compute_residual(u)
+        env.initial_residual = residual  # (reset(): _compute_initial_state sets it, sdc_env.py:306-314)
+        env.state = (residual, np.zeros_like(u))
+    return env

@@ -3,7 +3,8 @@
 Public surface (mirrors the reference's):
 
 * ``make(envname, num_envs=..., **kwargs)`` / ``SDCVecEnv`` - batched ``sdc-v0`` / ``sdc-v1`` envs with the
-  DummyVecEnv protocol (reference ``sdc_gym/__init__.py:3-13``, ``utils/utils.py:235-315``).
+  DummyVecEnv protocol (reference ``sdc_gym/__init__.py:3-13``, ``utils/utils.py:235-315``); ``sdc-v4``
+  (``SDCForceVecEnv``, ``sdc_gym/__init__.py:15-19``) composes the same kernels.
 * ``SpectralRadiusLoss`` / ``ResidualLoss`` - batched forward values of the ``dp_playground.py:186-258`` losses.
 * ``VecNormalize`` - device-side observation / reward normalisation (SB3 semantics).
 * ``collocation_matrix`` - the Gauss-Radau-right Q the reference takes from pySDC.
@@ -18,9 +19,10 @@ REGISTRY = {
     # id: (env kind, max_episode_steps)  - sdc_gym/__init__.py:3-13
     "sdc-v0": ("SDC_Full_Env", 1),
     "sdc-v1": ("SDC_Step_Env", 50),
+    "sdc-v4": ("SDC_Full_Force_Env", 50),  # sdc_gym/__init__.py:15-19 (force_env.py)
 }
 
-__all__ = ["make", "make_env", "SDCVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts",
+__all__ = ["make", "make_env", "SDCVecEnv", "SDCForceVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts",
            "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY", "register_gym"]
 
 
@@ -29,6 +31,9 @@ def __getattr__(name):
     if name == "SDCVecEnv":
         from .vec_env import SDCVecEnv
         return SDCVecEnv
+    if name == "SDCForceVecEnv":
+        from .force_env import SDCForceVecEnv
+        return SDCForceVecEnv
     if name in ("SpectralRadiusLoss", "ResidualLoss"):
         from . import loss
         return getattr(loss, name)
@@ -45,6 +50,9 @@ def make(envname, num_envs=1, **kwargs):
     """``gym.make(envname, **kwargs)`` for a whole batch: returns an ``SDCVecEnv`` with ``num_envs`` envs."""
     if envname not in REGISTRY:
         raise KeyError(f"unknown env id {envname!r}; registered: {sorted(REGISTRY)}")
+    if envname == "sdc-v4":
+        from .force_env import SDCForceVecEnv
+        return SDCForceVecEnv(envname, num_envs=num_envs, **kwargs)
     from .vec_env import SDCVecEnv
     return SDCVecEnv(envname, num_envs=num_envs, **kwargs)
 

@@ -76,5 +76,43 @@ class SingleEnv(_Base):
         self._vec.close()
 
 
+class SingleForceEnv(_Base):
+    """One ``SDC_Full_Force_Env`` (``sdc_force_env.py:7-118``): ``reset() -> (residual, zeros)``,
+    ``step(action) -> ((residual, diagonal), reward, done, info)`` with ``info['ntries']``."""
+
+    metadata = {"render.modes": []}
+
+    def __init__(self, envname="sdc-v4", **kwargs):
+        from .force_env import SDCForceVecEnv
+
+        kwargs.pop("num_envs", None)
+        self._vec = SDCForceVecEnv(envname, num_envs=1, autoreset=False, **kwargs)
+        self.observation_space = self._vec.observation_space
+        self.action_space = self._vec.action_space
+        self.max_tries = self._vec.max_tries
+
+    prec = property(lambda self: self._vec.prec)
+    restol = property(lambda self: self._vec.restol)
+    M = property(lambda self: self._vec.M)
+    ntries = property(lambda self: int(self._vec.ntries[0]))
+
+    def seed(self, seed=None):
+        self._vec.seed(seed)
+        return [seed]
+
+    def reset(self, **kwargs):
+        obs = self._vec.reset(**kwargs)
+        return (obs[0, 0], obs[0, 1])
+
+    def step(self, action):
+        obs, rew, done, infos = self._vec.step(np.asarray(action, dtype=np.float64).reshape(1, -1))
+        return (obs[0, 0], obs[0, 1]), float(rew[0]), bool(done[0]), infos[0]
+
+    def close(self):
+        self._vec.close()
+
+
 def make_single(envname="sdc-v0", **kwargs):
+    if envname == "sdc-v4":
+        return SingleForceEnv(envname, **kwargs)
     return SingleEnv(envname, **kwargs)

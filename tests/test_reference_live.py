@@ -46,3 +46,33 @@ def test_fixed_preconditioners_equal_reference():
         for prec in ("LU", "min", "EE", "zeros"):
             env = mod.SDC_Full_Env(M=M, dt=1.0, restol=1e-10, prec=prec)
             assert_same(np.asarray(env._get_prec(None), dtype=np.float64), fixed_preconditioner(prec, M), f"{prec} M={M}")
+
+
+@pytest.mark.skipif(not ref_loader.force_reference_available(), reason="reference sdc_force_env.py not present")
+def test_force_env_fixture_is_what_the_reference_produces():
+    """tests/golden/sdc_force_golden.npz (the parity anchor of ``sdc-v4``) against ``SDC_Full_Force_Env`` run live -
+    and the unrepaired class does fail the way DESIGN.md says (``sdc_force_env.py:77-82``)."""
+    import os
+    import warnings
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "sdc_force_golden.npz"))
+    for name, M, kw in (("m3_iter", 3, {}), ("m5_reschange", 5, dict(reward_iteration_only=False))):
+        g = {k.split("/", 1)[1]: gold[k] for k in gold.files if k.startswith(name + "/")}
+        for e in range(0, 24, 5):
+            env = ref_loader.make_reference_force_env(lam=g["lam"][e], M=M, dt=1.0, restol=1e-10,
+                                                      lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0], **kw)
+            assert_same(env.state[0], g["r0"][e])
+            for t in range(g["actions"].shape[1]):
+                if not g["valid"][e, t]:
+                    break
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    obs, rew, done, info = env.step(g["actions"][e, t])
+                assert_same(obs[0], g["res"][e, t]); assert_same(obs[1], g["diag"][e, t])
+                assert (rew, bool(done), info["niter"], info["ntries"]) == (g["reward"][e, t], bool(g["done"][e, t]),
+                                                                           g["niter"][e, t], g["ntries"][e, t])
+    raw = ref_loader.load_reference_force_env().SDC_Full_Force_Env(M=3, dt=1.0, restol=1e-10)
+    raw.reset()
+    with pytest.raises(TypeError), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # the MIN diagonal: the solve does not diverge -> reward_func(4 of its 6 arguments)
+        raw.step(2 * np.array([0.3203856825077055, 0.1399680686269595, 0.3716708461097372]) - 1)
