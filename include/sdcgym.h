@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SDCGYM_ABI_VERSION 7 /* 5: sweep_mode + work buffers in sdcgym_state; 6: in-kernel peer-memory statistics exchange; 7: sdcgym_state.norm_init */
+#define SDCGYM_ABI_VERSION 8 /* 5: sweep_mode + work buffers in sdcgym_state; 6: in-kernel peer-memory statistics exchange; 7: sdcgym_state.norm_init; 8: sdcgym_state.phase_* */
 #define SDCGYM_MAX_M 9
 #define SDCGYM_CERT_PLANES 8
 
@@ -88,6 +88,7 @@ extern "C" {
  *              u, r, ||r||, reward agree within rounding (<= 1e-12 relative).  Applies to sdc-v0 steps that start from
  *              an exact state (after reset / auto-reset); combinations without a certificate (sdc-v1, collect_states)
  *              run the exact kernel.  Needs the work buffers of sdcgym_state. */
+#define SDCGYM_PHASE_COUNTERS 8
 #define SDCGYM_SWEEP_EXACT 0
 #define SDCGYM_SWEEP_CERTIFIED 1
 
@@ -136,6 +137,13 @@ typedef struct sdcgym_state {
     float* cert;            /* [SDCGYM_CERT_PLANES][ld] per-env certificate constants, rewritten by every step */
     int32_t* fallback_list; /* [N] indices of the envs the exact kernel re-ran in the last step */
     int32_t* fallback_count; /* [2]: length of fallback_list for the last step, cumulative count over all steps */
+    /* optional work buffers of the PHASED full solve (all three or none; NULL = single-launch kernels).  sdc-v0 with a
+     * non-diagonal Q_delta, M <= 7, large batches: the envs of a warp stop after very different sweep counts, so the
+     * solve is cut at fixed sweep counts and every later pass runs over the compacted list of the envs still
+     * iterating (csrc/step_kernels.cuh, step_one PHASE).  Same sweep sequence per env, every output bit-identical. */
+    int32_t* phase_list;  /* [2][N] ping-pong lists of suspended envs (indices local to this state) */
+    int32_t* phase_count; /* [SDCGYM_PHASE_COUNTERS] list length per pass of the last step */
+    double* phase_pinv;   /* [2 M^2][ld] inverse of I - z Q_delta of the suspended envs */
 } sdcgym_state;
 
 /* Per-step inputs/outputs (device pointers; NULL outputs are skipped). */

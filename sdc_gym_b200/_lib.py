@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDCGYM_LIB") or os.path.join(_HERE, "libsdcgym.so")  # (SDCGYM_LIB: experiment builds)
 
 MAX_M = 9
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 ENV_KINDS = {"sdc-v0": 0, "sdc-v1": 1}
 PREC_TYPES = {"diag": 0, "lower_diag": 1, "lower_tri": 2, "strictly_lower_tri": 3, "fixed": 4}
@@ -29,6 +29,7 @@ BLAS_SKYLAKEX, BLAS_HASWELL = 0, 1
 ACTION_SCALE, ACTION_F32 = 1, 2  # bits of EnvDesc.do_scale (include/sdcgym.h)
 SWEEP_MODES = {"exact": 0, "certified": 1}
 CERT_PLANES = 8
+PHASE_COUNTERS = 8  # SDCGYM_PHASE_COUNTERS
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 
@@ -83,6 +84,9 @@ class State(ctypes.Structure):
         ("cert", ctypes.c_void_p),
         ("fallback_list", ctypes.c_void_p),
         ("fallback_count", ctypes.c_void_p),
+        ("phase_list", ctypes.c_void_p),
+        ("phase_count", ctypes.c_void_p),
+        ("phase_pinv", ctypes.c_void_p),
     ]
 
 

@@ -303,6 +303,8 @@ static int pipe_step_impl(sdcgym_pipe* p, const sdcgym_env_desc* desc, const sdc
         if (s2.norm_init) s2.norm_init += lo;
         if (s2.cert) s2.cert += lo;                    // certified sweep mode: per-chunk certificate planes and fallback list
         if (s2.fallback_list) s2.fallback_list += lo;  // (indices are local to the chunk)
+        if (s2.phase_list) s2.phase_list += 2 * lo;    // phased dense solve: [2][n] lists of the chunk, inverse planes
+        if (s2.phase_pinv) s2.phase_pinv += lo;
         sdcgym_step_io io = *dev;
         io.action = A > 0 ? act_dev + lo * aw : nullptr;
         io.action_env_stride = aw;
@@ -547,6 +549,8 @@ extern "C" int sdcgym_pipe_step_block(sdcgym_pipe* p, const sdcgym_env_desc* des
         if (s2.norm_init) s2.norm_init += lo;
         if (s2.cert) s2.cert += lo;                    // certified sweep mode: per-chunk certificate planes and fallback list
         if (s2.fallback_list) s2.fallback_list += lo;  // (indices are local to the chunk)
+        if (s2.phase_list) s2.phase_list += 2 * lo;    // phased dense solve: [2][n] lists of the chunk, inverse planes
+        if (s2.phase_pinv) s2.phase_pinv += lo;
         sdcgym_step_io io2 = io;
         if (A > 0) io2.action = bio->action_dev + lo * aw;
         io2.reward += lo;

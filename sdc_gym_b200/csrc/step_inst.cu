@@ -43,8 +43,95 @@ static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& con
     return cudaSuccess;
 }
 
+#ifndef SDCGYM_PHASE_MIN_N
+#define SDCGYM_PHASE_MIN_N 16384  // smallest batch that takes the phased dense solve (three more launches per step)
+#endif
+
+// Hand-over rules of the phased dense solve (step_one PHASE), one per pass but the last (which runs every env to its
+// end): a warp of pass k hands its stragglers over once they all have done stop[k] sweeps and fewer than lanes[k] of
+// its lanes are still iterating.  Defaults measured on B200 against the single launch (profiles/README.md).
+// Experiments: SDCGYM_PHASE_STOPS="a,b,..." (ascending sweep counts; alone: hand over at exactly these counts whatever
+// the occupancy), SDCGYM_PHASE_LANES="a,b,..." (occupancy thresholds; alone: from the first sweep on).  An empty
+// SDCGYM_PHASE_STOPS or SDCGYM_PHASE_LANES switches the phased solve off.  At most 6 hand-overs.
+struct PhasePlan {
+    int n = 2;
+    int stop[6] = {4, 12, 0, 0, 0, 0};
+    int lanes[6] = {8, 8, 0, 0, 0, 0};
+    static int parse(const char* e, int* out, bool ascending) {
+        int n = 0, prev = 0;
+        while (*e && n < 6) {
+            char* end = nullptr;
+            const long v = strtol(e, &end, 10);
+            if (end == e) break;
+            if (v > 0 && v < (1 << 20) && (!ascending || v > prev)) out[n++] = prev = (int)v;
+            e = (*end == ',') ? end + 1 : end;
+        }
+        return n;
+    }
+    PhasePlan() {
+        const char* es = getenv("SDCGYM_PHASE_STOPS");
+        const char* el = getenv("SDCGYM_PHASE_LANES");
+        if (!es && !el) return;
+        int st[6] = {0, 0, 0, 0, 0, 0}, ln[6] = {0, 0, 0, 0, 0, 0};
+        const int ns = es ? parse(es, st, true) : 0, nl = el ? parse(el, ln, false) : 0;
+        n = es ? (el ? (ns < nl ? ns : nl) : ns) : nl;
+        for (int k = 0; k < 6; k++) {
+            stop[k] = (k < n && es) ? st[k] : 0;    // no sweep count given: from the first sweep on
+            lanes[k] = (k < n) ? (el ? ln[k] : 33) : 0;  // no threshold given: whatever the occupancy
+        }
+    }
+};
+
+// sdc-v0, dense Q_delta, one env per thread: inverse + sweeps for every env until its warp hands over, then one pass
+// per further hand-over rule over the compacted list of the envs that are still iterating
+template <int V>
+static cudaError_t launch_phased_dense(const StepParams<kM>& p0, const PhasePlan& plan, cudaStream_t s) {
+    constexpr int hold = kHoldDense, minb = HoldPolicy<kM>::dense_minb, block = HoldPolicy<kM>::dense_block;
+    constexpr size_t smem = step_kernel_smem_bytes<kM, hold, block>();
+    auto first = step_phase_kernel<kM, V, hold, minb, block, 1>;
+    auto later = step_phase_kernel<kM, V, hold, minb, block, 2>;
+    static std::atomic<uint64_t> conf1{0}, conf2{0};
+    cudaError_t e = opt_in_smem(first, smem, conf1);
+    if (e != cudaSuccess) return e;
+    e = opt_in_smem(later, smem, conf2);
+    if (e != cudaSuccess) return e;
+    int32_t* const lists = p0.cont_list;
+    int32_t* const counts = p0.cont_count;
+    e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * SDCGYM_PHASE_COUNTERS, s);
+    if (e != cudaSuccess) return e;
+    StepParams<kM> p = p0;
+    p.it_stop = plan.stop[0];
+    p.min_lanes = plan.lanes[0];
+    p.cont_list = lists;
+    p.cont_count = counts;
+    const unsigned blocks = (unsigned)((p.N + block - 1) / block);
+    first<<<blocks, block, smem, s>>>(p, nullptr, nullptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the list lengths live on the device: every later pass is launched with one block per `block` envs of the whole
+    // batch, and the blocks past the end of the list return at once (a short fixed grid striding over the list
+    // measured 20-25 % slower: two to four list rounds per block, the last one mostly empty)
+    for (int j = 1; j <= plan.n; j++) {
+        if (plan.stop[j - 1] >= p0.max_iters) break;  // nobody was suspended
+        p.it_stop = (j < plan.n) ? plan.stop[j] : 0x7fffffff;
+        p.min_lanes = (j < plan.n) ? plan.lanes[j] : 0;
+        p.cont_list = lists + (int64_t)(j & 1) * p.N;
+        p.cont_count = counts + j;
+        later<<<blocks, block, smem, s>>>(p, lists + (int64_t)((j - 1) & 1) * p.N, counts + j - 1);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <int KIND, int V, bool DENSE>
 static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
+    if constexpr (DENSE && KIND == SDCGYM_ENV_FULL && kM < kTeamMinM) {
+        static const PhasePlan plan;
+        if (plan.n > 0 && p.cont_list && p.cont_count && p.pinv_scratch && p.old_states == nullptr &&
+            p.N >= SDCGYM_PHASE_MIN_N && p.N <= 0x7fffffff && p.max_iters > plan.stop[0])
+            return launch_phased_dense<V>(p, plan, s);
+    }
     if constexpr (DENSE && kM >= kTeamMinM) {
         // large dense Q_delta: one env per team of M lanes (team_kernels.cuh); collect_states keeps the per-thread kernel
         static const bool no_team = getenv("SDCGYM_NO_TEAM") != nullptr;  // A/B switch for tools/bench_dense.py

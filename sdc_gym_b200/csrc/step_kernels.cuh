@@ -49,6 +49,12 @@ struct StepParams {
     int64_t env_offset;
     int32_t prec_type, is_complex, do_scale, max_iters, strategy, autoreset, curriculum;
     double log_restol_nf;  // math.log(restol * norm_factor) (sdc_env.py:346), evaluated once on the host
+    // phased full solve (dense Q_delta, see step_one PHASE): sweep count at which a pass hands its unfinished envs over
+    int32_t it_stop;
+    int32_t min_lanes;     // ... and only while fewer than this many lanes of the warp are still iterating (33: always)
+    int32_t* cont_list;    // [<= N] indices of the envs this pass suspended (next pass's work list)
+    int32_t* cont_count;   // [1] length of cont_list (zeroed before the first pass)
+    double* pinv_scratch;  // [2 M^2][ld] inverse of P of the suspended envs (plane 2k: Re, 2k+1: Im of entry k = row*M+col)
 };
 
 // Where a step reads its per-env inputs from.  Default (nullptr): the global planes of StepParams, element `i`.  The
@@ -306,7 +312,17 @@ struct NoAfterLoads {
 
 // `after_loads` runs once every input of the env sits in registers (non-dense kernels): the streaming kernel releases
 // its shared-memory stage there and starts the next tile's copies.
-template <int M, int KIND, int V, bool DENSE, int HOLD, class AfterLoads = NoAfterLoads>
+//
+// PHASE (sdc-v0 full solve, dense Q_delta): envs of a warp stop after very different sweep counts (lower_tri, M = 5:
+// 39 % within 8 sweeps, 33 % run all 50; ncu: 18.6 of 32 lanes active, strictly_lower_tri 11.4), and a warp runs until
+// its last env is done.  The phased launch regroups the stragglers: PHASE 1 = first pass over all envs (inverse +
+// sweeps), PHASE 2 = a later pass over the compacted list of unfinished envs.  A warp hands over once all its running
+// envs have done p.it_stop sweeps and fewer than p.min_lanes of its lanes are still iterating (warps that stay busy
+// never hand over and cost nothing extra).  An env that is still running at the hand-over is SUSPENDED: its (u, r) go to the state planes, its sweep count to the niter plane (the
+// resnorm plane keeps the norm the divergence test compares against), the inverse to p.pinv_scratch (first pass only)
+// and its index to p.cont_list; a PHASE 2 pass picks it up with exactly those bits, so the sweep sequence of every
+// env - and therefore every output - is the one of the single-launch kernel.  PHASE 0 = no phases (unchanged code).
+template <int M, int KIND, int V, bool DENSE, int HOLD, class AfterLoads = NoAfterLoads, int PHASE = 0>
 SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1,
                         cplx* pside = nullptr, const int pstride = 1, const StepInputs* in = nullptr,
                         AfterLoads after_loads = AfterLoads()) {
@@ -351,7 +367,8 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     };
     if (!DENSE) load_state();  // the dense kernels need the registers for the inverse first
     double nr_old = in ? in->resnorm[ii] : p.resnorm[i];
-    int it = (KIND == SDCGYM_ENV_STEP) ? (in ? in->niter[ii] : p.niter[i]) : 0;
+    static_assert(PHASE == 0 || (DENSE && KIND == SDCGYM_ENV_FULL && HOLD != 5), "phased launches: dense full solves");
+    int it = (KIND == SDCGYM_ENV_STEP || PHASE == 2) ? (in ? in->niter[ii] : p.niter[i]) : 0;
     // the auto-reset needs these at the very end
     int32_t ep_old = p.autoreset ? (in ? in->episodes[ii] : p.episodes[i]) : 0;
     uint32_t ctr_old = p.autoreset ? (in ? in->rng_ctr[ii] : p.rng_ctr[i]) : 0u;
@@ -450,7 +467,14 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             const cplx d = qd_entry(r, c, act_index(r, c));
             return f32_qd ? cmul_np_f32(cplx{zr, zi}, d) : cmul_np(cplx{zr, zi}, d);
         };
-        if constexpr (M <= kRegInvMaxM) {
+        if constexpr (PHASE == 2) {
+            // resumed env: the inverse the first pass computed (same bits)
+#pragma unroll
+            for (int k = 0; k < M * M; k++) {
+                Pr[(DENSE && !PS) ? k : 0] = p.pinv_scratch[(2 * k) * ld + i];
+                Pi[(DENSE && !PS) ? k : 0] = p.pinv_scratch[(2 * k + 1) * ld + i];
+            }
+        } else if constexpr (M <= kRegInvMaxM) {
             RegMatrix<M> A;
 #pragma unroll
             for (int r = 0; r < M; r++)
@@ -627,7 +651,7 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         // while not done and niter < max_iters  (sdc_env.py:224-247); per-lane early exit by warp vote
         const HiBand bc = make_band(p.restol), be = make_band(thr);
         const SqBand sc = make_sqband(p.restol), se = make_sqband(thr);
-        bool act = p.max_iters > 0;
+        bool act = p.max_iters > 0 && (PHASE == 0 || valid);
         while (SDCGYM_WARP_ANY(act)) {
             if (act) {
                 it++;
@@ -664,6 +688,47 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 }
                 if (p.old_states && valid && it < p.max_iters) store_column<M>(p.old_states, i, p.max_iters, it, ur, ui, rr, ri);
                 act = !err && !conv && it < p.max_iters;
+            }
+            // hand-over: every env still iterating has done p.it_stop sweeps and the warp has thinned out to fewer
+            // than p.min_lanes of them (min_lanes > 32: at it_stop whatever the occupancy) - the stragglers are regrouped
+            if constexpr (PHASE != 0) {
+#ifdef __CUDA_ARCH__
+                const unsigned running = __ballot_sync(0xffffffffu, act);
+                const unsigned young = __ballot_sync(0xffffffffu, act && it < p.it_stop);
+                if (young == 0u && __popc(running) < p.min_lanes) break;
+#else
+                if (!(act && it < p.it_stop) && (act ? 1 : 0) < p.min_lanes) break;
+#endif
+            }
+        }
+        if constexpr (PHASE != 0) {
+            // still running at the hand-over count: suspend (the warp is converged here: the loop exit is a warp vote)
+            const bool susp = act;
+#ifdef __CUDA_ARCH__
+            const unsigned sm = __ballot_sync(0xffffffffu, susp);
+            if (sm) {
+                const int lane = (int)(threadIdx.x & 31u), leader = __ffs(sm) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(p.cont_count, __popc(sm));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (susp) p.cont_list[base + __popc(sm & ((1u << lane) - 1u))] = (int32_t)i;
+            }
+#else
+            if (susp) p.cont_list[p.cont_count[0]++] = (int32_t)i;
+#endif
+            if (susp) {
+                store_state<M>(p.S, ld, i, ur, ui, rr, ri);
+                p.niter[i] = it;
+                if constexpr (PHASE == 1) {
+                    const volatile double* ps = side;
+                    (void)ps;
+#pragma unroll
+                    for (int k = 0; k < M * M; k++) {
+                        p.pinv_scratch[(2 * k) * ld + i] = (HOLD == 9) ? ps[k * side_stride] : Pr[(DENSE && !PS) ? k : 0];
+                        p.pinv_scratch[(2 * k + 1) * ld + i] = (HOLD == 9) ? ps[(M * M + k) * side_stride] : Pi[(DENSE && !PS) ? k : 0];
+                    }
+                }
+                return;
             }
         }
         if (p.max_iters > 0) nr = inf_norm_fast<M>(rr, ri);
@@ -757,6 +822,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
         step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x, side_smem + threadIdx.x, BLOCK);
     } else {
         step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x);
+    }
+}
+
+// phased full solve of dense Q_delta (step_one PHASE): PHASE 1 = all envs, one per thread; PHASE 2 = the envs of
+// `list[0 .. *count)` (a fixed grid strides over the list, whose length only the device knows; threads past the end
+// run a clamped env that never sweeps and stores nothing)
+template <int M, int V, int HOLD, int MINB, int BLOCK, int PHASE>
+__global__ void __launch_bounds__(BLOCK, MINB) step_phase_kernel(const __grid_constant__ StepParams<M> p,
+                                                                 const int32_t* __restrict__ list,
+                                                                 const int32_t* __restrict__ count) {
+    static_assert(PHASE == 1 || PHASE == 2, "");
+    const int64_t n = (PHASE == 1) ? p.N : (int64_t)count[0];
+    for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < n; base += (int64_t)gridDim.x * BLOCK) {
+        const int64_t t = base + threadIdx.x;
+        const int64_t idx = (PHASE == 1) ? t : ((t < n) ? (int64_t)list[t] : p.N);
+        if constexpr (HOLD == 7) {
+            extern __shared__ double2 pside_smem[];
+            step_one<M, SDCGYM_ENV_FULL, V, true, HOLD, NoAfterLoads, PHASE>(p, idx, nullptr, 1, reinterpret_cast<cplx*>(pside_smem) + threadIdx.x, BLOCK);
+        } else if constexpr (HOLD >= 3) {
+            extern __shared__ double side_smem[];
+            step_one<M, SDCGYM_ENV_FULL, V, true, HOLD, NoAfterLoads, PHASE>(p, idx, side_smem + threadIdx.x, BLOCK);
+        } else {
+            step_one<M, SDCGYM_ENV_FULL, V, true, HOLD, NoAfterLoads, PHASE>(p, idx);
+        }
     }
 }
 

@@ -51,6 +51,12 @@ inline void fill_params(StepParams<M>& p, const sdcgym_env_desc* d, const sdcgym
     p.autoreset = d->autoreset;
     p.curriculum = d->curriculum;
     p.log_restol_nf = log(d->restol * d->norm_factor);
+    p.it_stop = 0x7fffffff;
+    p.min_lanes = 0;
+    // work buffers of the phased dense solve (launch_step decides whether to use them; single-launch kernels ignore them)
+    p.cont_list = st->phase_list;
+    p.cont_count = st->phase_count;
+    p.pinv_scratch = st->phase_pinv;
 }
 
 

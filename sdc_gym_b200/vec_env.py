@@ -29,6 +29,10 @@ from .precond import fixed_preconditioner, num_actions
 from .spaces import Box
 
 MAX_ITERS = 50  # SDC_Full_Env.max_iters, sdc_env.py:25
+PHASED_MAX_M = 7  # the phased dense solve covers the one-env-per-thread kernels (M >= 8: lane-team kernel)
+PHASED_MIN_ENVS = 16384  # smallest batch that allocates its work buffers (SDCGYM_PHASE_MIN_N in csrc/step_inst.cu)
+PHASED_TRIAL = 3  # phased=None: launches of each sequence per measurement (the first one untimed)
+PHASED_RETUNE = 512  # ... and device steps between two measurements
 MAX_EPISODE_STEPS = {"sdc-v0": 1, "sdc-v1": 50}  # sdc_gym/__init__.py:3-13
 
 
@@ -261,6 +265,7 @@ class SDCVecEnv:
         keep_terminal: bool = True,
         sweep_mode: str = "exact",
         lazy_info: bool = True,
+        phased: Optional[bool] = None,
     ):
         torch = _torch()
         if envname not in _lib.ENV_KINDS:
@@ -358,6 +363,29 @@ class SDCVecEnv:
                 self.cert = torch.zeros((_lib.CERT_PLANES, self.ld), dtype=torch.float32, device=dev)
                 self.fallback_list = torch.zeros(max(1, N), dtype=torch.int32, device=dev)
                 self.fallback_count = torch.zeros(2, dtype=torch.int32, device=dev)
+            # phased full solve (include/sdcgym.h: sdcgym_state.phase_*): sdc-v0 with a non-diagonal Q_delta - the envs
+            # of a warp stop after very different sweep counts, so large batches are solved in passes over compacted
+            # lists of the envs still iterating.  Bit-identical to the single launch; `phased=False` keeps that one.
+            dense = self.prec_type != "diag"
+            if prec is not None:
+                dense = bool(np.any(self.Qd_fixed != np.diag(np.diag(self.Qd_fixed))))
+            #   phased=None (default): large batches allocate the work buffers and `step_tensor` TIMES both launch
+            #   sequences on the caller's workload (CUDA events, no synchronisation) and keeps the faster one - the gain
+            #   depends on how unevenly the envs of a warp finish (measured: 1.5x when most envs stop after a few sweeps,
+            #   a few per cent slower when a third of them run all 50 sweeps; profiles/README.md);
+            #   phased=True: always the phased sequence.
+            want = (envname == "sdc-v0" and dense and self.M <= PHASED_MAX_M and not collect_states
+                    and N >= PHASED_MIN_ENVS) if phased is None else bool(phased)
+            self.phased = bool(want and envname == "sdc-v0" and dense and self.M <= PHASED_MAX_M and not collect_states)
+            self._phase_auto = self.phased and phased is None
+            self._phase_use = self.phased  # what the next device step launches
+            self._phase_trial = None       # running A/B measurement: {"ev": {True: [...], False: [...]}, "k": launches so far}
+            self._phase_next_trial = 0     # step count at which the next measurement starts
+            self.phase_timings = None      # (phased ms, single-launch ms) of the last completed measurement
+            if self.phased:
+                self.phase_list = torch.zeros(2 * max(1, N), dtype=torch.int32, device=dev)
+                self.phase_count = torch.zeros(_lib.PHASE_COUNTERS, dtype=torch.int32, device=dev)
+                self.phase_pinv = torch.empty((2 * self.M * self.M, self.ld), dtype=f64, device=dev)
         self._state_exact = True  # the stored (u, r) are bit-equal to the reference's (reset / exact step / injected)
         self._host = None  # pinned staging, allocated on first numpy-mode step
         self._snap = None
@@ -420,7 +448,7 @@ class SDCVecEnv:
     def _stream(self):
         return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
-    def _state(self, start=0, count=None):
+    def _state(self, start=0, count=None, use_phased=True):
         count = self.num_envs - start if count is None else count
         st = _lib.State()
         st.N, st.ld = count, self.ld
@@ -435,6 +463,10 @@ class SDCVecEnv:
             st.cert = self.cert.data_ptr() + 4 * start
             st.fallback_list = self.fallback_list.data_ptr() + 4 * start
             st.fallback_count = self.fallback_count.data_ptr()
+        if self.phased and use_phased:
+            st.phase_list = self.phase_list.data_ptr() + 8 * start
+            st.phase_count = self.phase_count.data_ptr()
+            st.phase_pinv = self.phase_pinv.data_ptr() + 8 * start
         return st
 
     def _desc_for(self, start):
@@ -598,11 +630,46 @@ class SDCVecEnv:
         io.terminal_obs = (self.terminal.data_ptr() + 8 * start) if (want_terminal and self.terminal is not None) else None
         io.old_states = (self.old_states.data_ptr() + 8 * start * 2 * self.M * self.max_iters * 2
                          if self.old_states is not None else None)
-        st = self._state(start, count)
+        whole = self.phased and start == 0 and count == self.num_envs
+        use_phased, ev = (self._phase_pick() if whole and self._phase_auto else (self.phased, None))
+        st = self._state(start, count, use_phased)
         d = self._desc_for(start)
         self._certified_step_begins()
+        if ev is not None:
+            ev[0].record(_torch().cuda.current_stream(self.device))
         _lib.check(self._L.sdcgym_step(ctypes.byref(d), ctypes.byref(st), ctypes.byref(io), self._stream()),
                    "sdcgym_step")
+        if ev is not None:
+            ev[1].record(_torch().cuda.current_stream(self.device))
+
+    def _phase_pick(self):
+        """phased=None: which launch sequence this device step takes, and the event pair that times it (or None).
+
+        A measurement is PHASED_TRIAL launches of each sequence, alternating, the first of each untimed; it is read
+        back without blocking once all its events have completed, and repeated every PHASED_RETUNE steps (the
+        workload of a learning policy drifts).  Results are bit-identical either way: only the speed is chosen."""
+        torch = _torch()
+        t = self._phase_trial
+        if t is None and self._step_count >= self._phase_next_trial:
+            t = self._phase_trial = {"ev": {True: [], False: []}, "k": 0}
+        if t is None:
+            return self._phase_use, None
+        if t["k"] < 2 * PHASED_TRIAL:
+            which = (t["k"] % 2 == 0)
+            timed = t["k"] >= 2
+            t["k"] += 1
+            if not timed:
+                return which, None
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            t["ev"][which].append(ev)
+            return which, ev
+        if all(e[1].query() for evs in t["ev"].values() for e in evs):
+            ms = {w: min(e[0].elapsed_time(e[1]) for e in evs) for w, evs in t["ev"].items()}
+            self.phase_timings = (ms[True], ms[False])
+            self._phase_use = ms[True] < ms[False]
+            self._phase_trial = None
+            self._phase_next_trial = self._step_count + PHASED_RETUNE
+        return self._phase_use, None
 
     @_lib.on_device
     def step_tensor(self, actions=None, want_terminal=True):
@@ -797,6 +864,11 @@ class SDCVecEnv:
         src = self._stage_actions(host, actions) if self._kernel_n_act > 0 else None
         hs, owned = self._acquire_set(host)
         bio, st = self._block_io()
+        if self.phased:  # phased=None: follow what the device steps measured (the struct is cached)
+            on = self._phase_use
+            st.phase_list = self.phase_list.data_ptr() if on else None
+            st.phase_count = self.phase_count.data_ptr() if on else None
+            st.phase_pinv = self.phase_pinv.data_ptr() if on else None
         bio.host_block = hs.ptr
         bio.action_host = src.data_ptr() if src is not None else None
         self._certified_step_begins()

@@ -47,6 +47,7 @@ def shim():
         L.shim_step_hold9.argtypes = L.shim_step.argtypes
         L.shim_spectral_radius.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64, vp, vp, vp]
         L.shim_step_certified.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int]
+        L.shim_step_phased.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int]
         _shim = L
     return _shim
 
@@ -103,6 +104,11 @@ class ShimBatch:
         self.fallback_list = np.zeros(max(1, n), np.int32)
         self.fallback_count = np.zeros(2, np.int32)
         self.trace = None
+        # work buffers of the phased dense solve (poisoned: a pass may only read what an earlier pass wrote)
+        self.phase_list = np.full(2 * max(1, n), -1, np.int32)
+        self.phase_count = np.full(_lib.PHASE_COUNTERS, -1, np.int32)
+        self.phase_pinv = np.full((2 * M * M, ld), np.nan)
+        self.phase_stops = (6, 16)
 
     def _state(self):
         st = _lib.State()
@@ -112,6 +118,8 @@ class ShimBatch:
         st.norm_init = None if self.norm_init is None else self.norm_init.ctypes.data
         st.cert, st.fallback_list = self.cert.ctypes.data, self.fallback_list.ctypes.data
         st.fallback_count = self.fallback_count.ctypes.data
+        st.phase_list, st.phase_count = self.phase_list.ctypes.data, self.phase_count.ctypes.data
+        st.phase_pinv = self.phase_pinv.ctypes.data
         return st
 
     def reset(self, lam=None, mask=None):
@@ -154,6 +162,10 @@ class ShimBatch:
             self.trace = np.full((self.n, self.d.max_iters, 2 * self.M + 2), np.nan)
             rc = shim().shim_step_certified(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io),
                                             self.trace.ctypes.data, int(getattr(self, "run_fallback", True)))
+        elif self.entry == "shim_step_phased":
+            stops = np.asarray(self.phase_stops, np.int32)
+            rc = shim().shim_step_phased(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io),
+                                         stops.ctypes.data, len(stops))
         else:
             rc = getattr(shim(), self.entry)(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
         assert rc == 0

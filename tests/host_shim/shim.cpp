@@ -76,6 +76,62 @@ static int step_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym
 }
 
 
+// phased dense full solve (step_one PHASE), the pass sequence of launch_phased_dense (csrc/step_inst.cu) with the
+// "threads" of every pass run one after the other; needs sdcgym_state.phase_*
+template <int M>
+static int step_phased_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io, const int* stops,
+                         int nstops) {
+    if constexpr (M <= 7) {
+        StepParams<M> p;
+        fill_params<M>(p, d, st);
+        fill_step_io<M>(p, io);
+        if (!p.cont_list || !p.cont_count || !p.pinv_scratch || nstops < 1) return -3;
+        constexpr int HS = HoldPolicy<M>::dense;
+        double side[3 * 2 * M * M];  // stride 3
+        cplx pside[3 * 2 * M * M];
+        int32_t* const lists = p.cont_list;
+        int32_t* const counts = p.cont_count;
+        for (int k = 0; k < SDCGYM_PHASE_COUNTERS; k++) counts[k] = 0;
+        const int64_t nthreads = (p.N + kBlock - 1) / kBlock * kBlock;
+        p.it_stop = stops[0];
+        p.min_lanes = 33;  // at the sweep count, whatever the occupancy (the host build has no warps)
+        p.cont_count = counts;
+        for (int64_t i = 0; i < nthreads; i++) {
+            if (d->blas_variant == 0) step_one<M, 0, 0, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
+            else step_one<M, 0, 1, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
+        }
+        for (int j = 1; j <= nstops; j++) {
+            if (stops[j - 1] >= p.max_iters) break;
+            p.it_stop = (j < nstops) ? stops[j] : 0x7fffffff;
+            p.min_lanes = (j < nstops) ? 33 : 0;
+            p.cont_list = lists + (int64_t)(j & 1) * p.N;
+            p.cont_count = counts + j;
+            const int32_t* in = lists + (int64_t)((j - 1) & 1) * p.N;
+            const int64_t n = counts[j - 1], nt = (n + kBlock - 1) / kBlock * kBlock;
+            for (int64_t t = 0; t < nt; t++) {
+                const int64_t idx = t < n ? (int64_t)in[t] : p.N;
+                if (d->blas_variant == 0) step_one<M, 0, 0, true, HS, NoAfterLoads, 2>(p, idx, side, 3, pside, 3);
+                else step_one<M, 0, 1, true, HS, NoAfterLoads, 2>(p, idx, side, 3, pside, 3);
+            }
+        }
+        return 0;
+    }
+    return -2;
+}
+extern "C" int shim_step_phased(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io,
+                                const int* stops, int nstops) {
+    if (d->env_kind != SDCGYM_ENV_FULL) return -2;
+    switch (d->M) {
+    case 2: return step_phased_m<2>(d, st, io, stops, nstops);
+    case 3: return step_phased_m<3>(d, st, io, stops, nstops);
+    case 4: return step_phased_m<4>(d, st, io, stops, nstops);
+    case 5: return step_phased_m<5>(d, st, io, stops, nstops);
+    case 6: return step_phased_m<6>(d, st, io, stops, nstops);
+    case 7: return step_phased_m<7>(d, st, io, stops, nstops);
+    }
+    return -2;
+}
+
 extern "C" int shim_reset(const sdcgym_env_desc* d, const sdcgym_state* st, const double* lam_in, const uint8_t* mask,
                           double* old_states) {
     switch (d->M) {
