@@ -252,29 +252,43 @@ def run_secondary(torch, np, dev, rank, world, barrier, max_over_ranks, fp64_pea
     for Mx in (3, 5, 7, 9):
         for pt in ("lower_tri", "strictly_lower_tri"):
             A = num_actions(Mx, pt)
-            env = sdc_gym_b200.make("sdc-v0", num_envs=Ns, M=Mx, prec_type=pt, do_scale=False, env_offset=rank * Ns, **KW)
-            env.reset()
             acts = [torch.rand((Ns, A), dtype=torch.float64, device=dev, generator=gen) * 0.3 for _ in range(2)]
-            k = [0]
+            # M <= 7: both launch sequences of the dense full solve (bit-identical results; SDCVecEnv's default times
+            # them on the caller's workload and keeps the faster one, which is what `ms_per_step` reports)
+            by_launch = {}
+            for phased in ((False, True) if Mx <= 7 else (False,)):
+                env = sdc_gym_b200.make("sdc-v0", num_envs=Ns, M=Mx, prec_type=pt, do_scale=False, env_offset=rank * Ns,
+                                        phased=phased, **KW)
+                env.reset()
+                k = [0]
 
-            def f():
-                k[0] += 1
-                env.step_tensor(acts[k[0] % 2])
+                def f():
+                    k[0] += 1
+                    env.step_tensor(acts[k[0] % 2])
 
-            ms = timed(f, 3)
-            sum_niter = allsum(env.info_niter[:Ns].double().sum())
+                by_launch["phased" if phased else "single"] = timed(f, 3)
+                sum_niter = allsum(env.info_niter[:Ns].double().sum())
+                if phased:
+                    suspended = [int(c) for c in env.phase_count.cpu().numpy()[:2]]
+                del env
+            launch = min(by_launch, key=by_launch.get)
+            ms = by_launch[launch]
             per_sweep = 8 * Mx * Mx + (18 if pt == "lower_tri" else 12) * Mx
             flops = sum_niter * per_sweep + world * Ns * (15 * Mx + 2 * A)
             tf = flops / (ms * 1e-3) / 1e12
             sweep.append({"M": Mx, "prec_type": pt, "envs_per_gpu": Ns, "ms_per_step": ms,
                           "env_steps_per_s": world * Ns / ms * 1e3, "mean_niter": sum_niter / (world * Ns),
-                          "fp64_tflops_algorithmic": tf, "fp64_frac": tf / (world * fp64_peak) if fp64_peak else None})
-            del env, acts
+                          "fp64_tflops_algorithmic": tf, "fp64_frac": tf / (world * fp64_peak) if fp64_peak else None,
+                          "launch": launch, "ms_by_launch": by_launch,
+                          "suspended_per_pass_rank0": suspended if Mx <= 7 else None})
+            del acts
             torch.cuda.empty_cache()
     out["config3_dense_qdelta_sweep"] = {
         "workload": "sdc-v0, Q_delta entries ~ U[0, 0.3] (do_scale=False), lambda ~ U[-100,0] + i U[-10,0]", "cases": sweep,
         "flops": "per sweep 8M^2+18M (lower_tri) / 8M^2+12M (strictly_lower_tri), set-up 15M + 2A (SURVEY 8d); the "
-                 "bit-exact kernels execute more (the pivoted zgetf2 + ztrsm emulation of np.linalg.inv per step)"}
+                 "bit-exact kernels execute more (the pivoted zgetf2 + ztrsm emulation of np.linalg.inv per step)",
+        "launch": "single = one kernel, a warp runs until its last env is done; phased = warps that have thinned out "
+                  "hand their stragglers to compacted lists (csrc/step_kernels.cuh step_one PHASE); M >= 8: lane-team kernel"}
     # ---- the certified substitution sweep mode (SDCGYM_SWEEP_CERTIFIED) against the exact mode on the headline workload
     #      and on a workload where half of the envs converge (actions near the MIN preconditioner) ----
     Nc = ENVS_PER_GPU

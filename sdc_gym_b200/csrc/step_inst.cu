@@ -54,9 +54,11 @@ static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& con
 // the occupancy), SDCGYM_PHASE_LANES="a,b,..." (occupancy thresholds; alone: from the first sweep on).  An empty
 // SDCGYM_PHASE_STOPS or SDCGYM_PHASE_LANES switches the phased solve off.  At most 6 hand-overs.
 struct PhasePlan {
-    int n = 2;
-    int stop[6] = {4, 12, 0, 0, 0, 0};
-    int lanes[6] = {8, 8, 0, 0, 0, 0};
+    // one hand-over: every further pass ends with a tail of a few warps that run up to 45 dependent sweeps (>= 60 us);
+    // 2^22 envs, M = 3 / 5 / 7: strictly_lower_tri 1.41 / 1.54 / 1.51 x, lower_tri 0.92 / 0.95 / 0.97 x the single launch
+    int n = 1;
+    int stop[6] = {5, 0, 0, 0, 0, 0};
+    int lanes[6] = {8, 0, 0, 0, 0, 0};
     static int parse(const char* e, int* out, bool ascending) {
         int n = 0, prev = 0;
         while (*e && n < 6) {

@@ -58,9 +58,9 @@ def test_phased_solve_is_bit_identical_to_the_single_launch(M, prec_type):
         act = rng.uniform(0, 0.3, (n, num_actions(M, prec_type)))
         out = _same_step(a, b, act)
         c = b.phase_count.cpu().numpy()
-        # default plan: two hand-overs (warps that have thinned out after 4 / 12 sweeps), the last pass runs every env
-        # it gets to its end
-        assert 0 <= c[1] <= c[0] < n and c[2] == 0
+        # default plan: one hand-over (warps that have thinned out after 5 sweeps), the second pass runs every env it
+        # gets to its end
+        assert 0 <= c[0] < n and c[1] == 0
         if prec_type == "strictly_lower_tri":
             assert c[0] > 0
 
