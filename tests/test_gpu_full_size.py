@@ -17,11 +17,16 @@ KW = dict(dt=1.0, restol=1e-10, lambda_real_interval=[-100, 0], lambda_imag_inte
 
 @pytest.mark.parametrize("M", [3, 5, 7, 9])
 @pytest.mark.parametrize("prec_type", ["lower_tri", "strictly_lower_tri"])
-def test_config2_m_sweep_triangular_4m_envs(M, prec_type):
-    """config 2: M sweep 3/5/7/9 with lower_tri and strictly_lower_tri Q_delta, 4M envs on one GPU"""
+@pytest.mark.parametrize("phased", [False, True])
+def test_config2_m_sweep_triangular_4m_envs(M, prec_type, phased):
+    """config 2: M sweep 3/5/7/9 with lower_tri and strictly_lower_tri Q_delta, 4M envs on one GPU; single launch and
+    phased solve (M <= 7)"""
     import torch
+    if phased and M > 7:
+        pytest.skip("M >= 8 runs the lane-team kernel")
     n = 1 << 22
-    env = sdc_gym_b200.make("sdc-v0", num_envs=n, M=M, prec_type=prec_type, do_scale=False, seed=M, **KW)
+    env = sdc_gym_b200.make("sdc-v0", num_envs=n, M=M, prec_type=prec_type, do_scale=False, seed=M, phased=phased, **KW)
+    assert env.phased == phased
     env.reset()
     lam0 = torch.view_as_complex(torch.stack([env.lam[0, :n], env.lam[1, :n]], dim=1).contiguous()).clone()
     A = num_actions(M, prec_type)

@@ -170,6 +170,20 @@ def test_env_on_a_device_that_is_not_current():
     lam = rng.uniform(-100, 0, 64) + 1j * rng.uniform(-10, 0, 64)
     d = rng.uniform(0, 1, (64, 5))
     assert torch.equal(l0.spectral_radii(lam, d).cpu(), l1.spectral_radii(lam, d).cpu())
+    # the phased dense solve (two more kernels with a > 48 KB shared-memory opt-in) on the device that is not current
+    from sdc_gym_b200.precond import num_actions
+
+    n2 = 20000
+    kw2 = dict(M=5, prec_type="strictly_lower_tri", do_scale=False, seed=2, **{k: v for k, v in KW.items() if k != "M"})
+    p0 = sdc_gym_b200.make("sdc-v0", num_envs=n2, device="cuda:0", phased=False, **kw2)
+    p1 = sdc_gym_b200.make("sdc-v0", num_envs=n2, device="cuda:1", phased=True, **kw2)
+    p0.reset()
+    p1.reset()
+    a2 = rng.uniform(0, 0.3, (n2, num_actions(5, "strictly_lower_tri")))
+    q0 = p0.step_tensor(torch.as_tensor(a2, device="cuda:0"))
+    q1 = p1.step_tensor(torch.as_tensor(a2, device="cuda:1"))
+    assert torch.equal(q0["niter"].cpu(), q1["niter"].cpu()) and torch.equal(p0.S.cpu().view(torch.int64), p1.S.cpu().view(torch.int64))
+    assert int(p1.phase_count[0]) > 0 and torch.cuda.current_device() == 0
     v1 = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=64, seed=1, device="cuda:1", **KW))
     v1.reset()
     v1.step(rng.uniform(-1, 1, (64, 5)))
