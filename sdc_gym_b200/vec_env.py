@@ -649,6 +649,8 @@ class SDCVecEnv:
         back without blocking once all its events have completed, and repeated every PHASED_RETUNE steps (the
         workload of a learning policy drifts).  Results are bit-identical either way: only the speed is chosen."""
         torch = _torch()
+        if torch.cuda.is_current_stream_capturing():  # inside a CUDA graph capture: no events, no queries
+            return self._phase_use, None
         t = self._phase_trial
         if t is None and self._step_count >= self._phase_next_trial:
             t = self._phase_trial = {"ev": {True: [], False: []}, "k": 0}

@@ -197,3 +197,42 @@ def test_other_hand_over_rules(plan):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _OTHER_STOPS], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kind,kw", [("sdc-v0", dict(prec_type="strictly_lower_tri", do_scale=False, phased=True)),
+                                     ("sdc-v0", dict(prec_type="lower_tri", do_scale=False)),  # phased=None: no timing inside a capture
+                                     ("sdc-v0", dict()), ("sdc-v1", dict())])
+def test_device_steps_can_be_captured_in_a_cuda_graph(kind, kw):
+    """the device-resident step is stream-ordered launches (and one memset for the phased solve): capturable; a replayed
+    graph of three steps equals three eager steps bit for bit"""
+    M, n = 5, 1 << 16
+    mk = lambda: sdc_gym_b200.make(kind, num_envs=n, M=M, seed=8, **{**KW, **kw})
+    a, b = mk(), mk()
+    a.reset()
+    b.reset()
+    A = a.n_act
+    hi = 0.3 if kw.get("do_scale") is False else 1.0
+    gen = torch.Generator(device=a.device)
+    gen.manual_seed(4)
+    acts = [torch.rand((n, A), dtype=torch.float64, device=a.device, generator=gen) * hi for _ in range(4)]
+    for e in (a, b):  # first launches configure the kernels (shared-memory opt-in): outside the capture
+        e.step_tensor(acts[3])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for k in range(3):
+                b.step_tensor(acts[k])
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(3):
+        out = a.step_tensor(acts[k])
+    g.replay()
+    torch.cuda.synchronize()
+    for name in STATE:
+        va, vb = getattr(a, name), getattr(b, name)
+        if va.is_floating_point():
+            va, vb = va.view(torch.int64), vb.view(torch.int64)
+        assert torch.equal(va, vb), name
+    assert torch.equal(a.info_niter, b.info_niter) and torch.equal(a.reward.view(torch.int64), b.reward.view(torch.int64))
