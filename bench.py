@@ -368,6 +368,49 @@ def run_secondary(torch, np, dev, rank, world, barrier, max_over_ranks, fp64_pea
         "policy": "uniform random actions drawn on the device", "normaliser_sync": "every step, all ranks"}
     del env, buf
     torch.cuda.empty_cache()
+    # ---- the same collection as ONE CUDA-graph replay per rollout (sdc_gym_b200.rollout.GraphedRollout; single rank:
+    #      the in-kernel peer exchange is sequenced from the host), at the benchmark size and in the reference's own
+    #      regime of 8 envs (BASELINE config 1), where launches and the interpreter are the whole cost ----
+    if world == 1:
+        from sdc_gym_b200.rollout import GraphedRollout
+
+        graphed = []
+        for Ng in (8, 16384, Nr):
+            def gpolicy(obs_planes, Ng=Ng):  # default CUDA generator: capturable
+                return torch.empty((Ng, 5), dtype=torch.float64, device=dev).uniform_(-1.0, 1.0), obs_planes[0], None
+
+            rec = {"envs": Ng, "n_steps": T}
+            for mode in ("eager", "graph"):
+                env = sdc_gym_b200.VecNormalize(sdc_gym_b200.make("sdc-v1", num_envs=Ng, M=5, reward_iteration_only=False,
+                                                                  output="torch", **KW))
+                env.reset()
+                gr = GraphedRollout(env, gpolicy, T, warmup=2) if mode == "graph" else None
+                b = [None]
+
+                def once():
+                    if gr is not None:
+                        gr.collect()
+                    else:
+                        b[0] = collect_rollouts(env, gpolicy, T, buffer=b[0])
+
+                for _ in range(4):
+                    once()
+                torch.cuda.synchronize()
+                reps = 5 if Ng == Nr else 30
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    once()
+                torch.cuda.synchronize()
+                ms_g = (time.perf_counter() - t0) / reps * 1e3  # wall clock: the interpreter is what the graph removes
+                rec[mode + "_ms_per_rollout"] = ms_g
+                rec[mode + "_env_steps_per_s"] = Ng * T / ms_g * 1e3
+                del env, gr, b
+            graphed.append(rec)
+        out["config5_graphed_rollout"] = {
+            "cases": graphed, "timing": "wall clock around back-to-back rollouts, synchronised at both ends",
+            "note": "bit-identical to the eager collection (tests/test_gpu_normalize_loss.py); BASELINE.md: the reference's "
+                    "sdc-v1 8-env rollout runs at ~1.2e4 env-steps/s per host core"}
+        torch.cuda.empty_cache()
     return out
 
 

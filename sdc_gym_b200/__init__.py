@@ -22,7 +22,7 @@ REGISTRY = {
     "sdc-v4": ("SDC_Full_Force_Env", 50),  # sdc_gym/__init__.py:15-19 (force_env.py)
 }
 
-__all__ = ["make", "make_env", "SDCVecEnv", "SDCForceVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts",
+__all__ = ["make", "make_env", "SDCVecEnv", "SDCForceVecEnv", "SpectralRadiusLoss", "ResidualLoss", "VecNormalize", "VecCheckNan", "RolloutBuffer", "collect_rollouts", "GraphedRollout",
            "collocation_matrix", "CollGaussRadauRight", "fixed_preconditioner", "num_actions", "REGISTRY", "register_gym"]
 
 
@@ -40,7 +40,7 @@ def __getattr__(name):
     if name in ("VecNormalize", "VecCheckNan"):
         from . import vec_normalize
         return getattr(vec_normalize, name)
-    if name in ("RolloutBuffer", "collect_rollouts"):
+    if name in ("RolloutBuffer", "collect_rollouts", "GraphedRollout"):
         from . import rollout
         return getattr(rollout, name)
     raise AttributeError(name)

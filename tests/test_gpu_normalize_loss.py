@@ -427,3 +427,46 @@ def test_residual_loss_gradient_against_finite_differences(prec_type):
     assert abs((fp - fm) / (2 * h) - an) <= 1e-5 * abs(an), ((fp - fm) / (2 * h), an)
     (_, _, _), g_r = loss.value_and_grad(lam, out.real.copy(), None, u0, u, res)
     assert not g_r.is_complex() and g_r.shape == (B, A)
+
+
+@pytest.mark.parametrize("normalised", [True, False])
+def test_graphed_rollout_replays_what_the_eager_collection_does(normalised):
+    """GraphedRollout: the whole collect_rollouts loop (policy, env steps, statistics, normalisation, buffer writes,
+    GAE) captured once and replayed - five consecutive rollouts bit-identical to five eager ones, episodes carried
+    over from one rollout to the next"""
+    import torch
+    from sdc_gym_b200.rollout import GraphedRollout, collect_rollouts
+
+    n, T = 4096, 6
+    w = torch.linspace(-1.0, 1.0, 20, dtype=torch.float64, device="cuda")
+
+    def policy(obs_planes):  # deterministic and capturable: plain torch ops on the observation planes
+        s = torch.tanh((obs_planes * w[:, None]).sum(0))
+        a = torch.stack([torch.tanh(s * (k + 1) * 0.7) for k in range(5)], dim=1) * 0.9
+        return a, s * 0.1, s * 0.01
+
+    def make():
+        e = sdc_gym_b200.make("sdc-v1", num_envs=n, seed=7, output="torch", reward_iteration_only=False, **KW)
+        e = sdc_gym_b200.VecNormalize(e) if normalised else e
+        e.reset()
+        return e
+
+    ea, eb = make(), make()
+    gr = GraphedRollout(eb, policy, T, warmup=2)
+    buf_a = None
+    for k in range(5):
+        buf_a = collect_rollouts(ea, policy, T, buffer=buf_a)
+        buf_b = gr.collect()
+        torch.cuda.synchronize()
+        for name in ("observations", "actions", "rewards", "values", "log_probs", "episode_starts", "advantages", "returns"):
+            ta, tb = getattr(buf_a, name), getattr(buf_b, name)
+            if ta.is_floating_point():
+                ta, tb = ta.view(torch.int64), tb.view(torch.int64)
+            assert torch.equal(ta, tb), (k, name)
+        assert buf_b.full and buf_b.pos == T
+    assert gr.replays == 3  # two eager warm-ups, then capture + replay, then replays
+    va, vb = getattr(ea, "venv", ea), getattr(eb, "venv", eb)
+    assert torch.equal(va.S.view(torch.int64), vb.S.view(torch.int64)) and torch.equal(va.episodes, vb.episodes)
+    assert int(buf_b.episode_starts.sum()) > 0
+    if normalised:
+        assert torch.equal(ea.obs_rms.mean, eb.obs_rms.mean) and torch.equal(ea.ret_rms.var, eb.ret_rms.var)
