@@ -43,9 +43,6 @@ static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& con
     return cudaSuccess;
 }
 
-#ifndef SDCGYM_PHASE_MIN_N
-#define SDCGYM_PHASE_MIN_N 16384  // smallest batch that takes the phased dense solve (three more launches per step)
-#endif
 
 // Hand-over rules of the phased dense solve (step_one PHASE), one per pass but the last (which runs every env to its
 // end): a warp of pass k hands its stragglers over once they all have done stop[k] sweeps and fewer than lanes[k] of
@@ -131,7 +128,8 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     if constexpr (DENSE && KIND == SDCGYM_ENV_FULL && kM < kTeamMinM) {
         static const PhasePlan plan;
         if (plan.n > 0 && p.cont_list && p.cont_count && p.pinv_scratch && p.old_states == nullptr &&
-            p.N >= SDCGYM_PHASE_MIN_N && p.N <= 0x7fffffff && p.max_iters > plan.stop[0])
+            p.N <= 0x7fffffff && p.max_iters > plan.stop[0])  // (the caller decides by passing the work buffers: the host
+            // layer does so from 16 384 envs on - below that the second launch costs more than it saves)
             return launch_phased_dense<V>(p, plan, s);
     }
     if constexpr (DENSE && kM >= kTeamMinM) {

@@ -30,7 +30,7 @@ from .spaces import Box
 
 MAX_ITERS = 50  # SDC_Full_Env.max_iters, sdc_env.py:25
 PHASED_MAX_M = 7  # the phased dense solve covers the one-env-per-thread kernels (M >= 8: lane-team kernel)
-PHASED_MIN_ENVS = 16384  # smallest batch that allocates its work buffers (SDCGYM_PHASE_MIN_N in csrc/step_inst.cu)
+PHASED_MIN_ENVS = 16384  # smallest batch that allocates the work buffers by default (phased=True: any batch)
 PHASED_TRIAL = 3  # phased=None: launches of each sequence per measurement (the first one untimed)
 PHASED_RETUNE = 512  # ... and device steps between two measurements
 MAX_EPISODE_STEPS = {"sdc-v0": 1, "sdc-v1": 50}  # sdc_gym/__init__.py:3-13
@@ -376,6 +376,10 @@ class SDCVecEnv:
             #   phased=True: always the phased sequence.
             want = (envname == "sdc-v0" and dense and self.M <= PHASED_MAX_M and not collect_states
                     and N >= PHASED_MIN_ENVS) if phased is None else bool(phased)
+            if want and phased is None:
+                # the work planes (2 M^2 doubles + two list entries per env) are only worth a quarter of the free memory
+                need = (2 * self.M * self.M * 8 + 8) * self.ld
+                want = need <= torch.cuda.mem_get_info(dev)[0] // 4
             self.phased = bool(want and envname == "sdc-v0" and dense and self.M <= PHASED_MAX_M and not collect_states)
             self._phase_auto = self.phased and phased is None
             self._phase_use = self.phased  # what the next device step launches

@@ -150,6 +150,8 @@ def test_default_times_both_launch_sequences_and_keeps_one():
 def test_small_batches_and_team_sizes_keep_the_single_launch():
     e = sdc_gym_b200.make("sdc-v0", num_envs=64, M=5, prec_type="lower_tri", **KW)
     assert not e.phased
+    e = sdc_gym_b200.make("sdc-v0", num_envs=64, M=5, prec_type="lower_tri", phased=True, **KW)
+    assert e.phased  # (explicitly asked for: any batch size)
     e = sdc_gym_b200.make("sdc-v0", num_envs=20000, M=9, prec_type="lower_tri", **KW)
     assert not e.phased
     e = sdc_gym_b200.make("sdc-v0", num_envs=20000, M=5, prec_type="diag", **KW)
@@ -236,3 +238,11 @@ def test_device_steps_can_be_captured_in_a_cuda_graph(kind, kw):
             va, vb = va.view(torch.int64), vb.view(torch.int64)
         assert torch.equal(va, vb), name
     assert torch.equal(a.info_niter, b.info_niter) and torch.equal(a.reward.view(torch.int64), b.reward.view(torch.int64))
+
+
+@pytest.mark.parametrize("n", [1, 33, 129, 1000])
+def test_tiny_batches_when_asked_for(n):
+    a, b = _pair(5, n, prec_type="strictly_lower_tri", do_scale=False)
+    rng = np.random.default_rng(n)
+    for s in range(3):
+        _same_step(a, b, rng.uniform(0, 0.3, (n, num_actions(5, "strictly_lower_tri"))))
