@@ -355,6 +355,22 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             }
         }
     }
+#ifdef __CUDA_ARCH__
+    if constexpr (DENSE) {
+        // the Q_delta entries are read one by one while P is built (an action row is M(M+1)/2 doubles at most per
+        // env, too many to hold next to the LU factors): without this the first pass over P is a chain of exposed
+        // load latencies (ncu: 14 % of the samples of the M = 5 lower_tri kernel on the first load uses).  Pull the
+        // row's cache lines into L1 now; the loads below then hit.
+        if (p.action && p.prec_type != SDCGYM_PREC_FIXED) {
+            const double* row = p.action + i * p.a_es;
+            constexpr int kMaxLines = (M * (M + 1) * 8 + 127) / 128 + 1;  // complex lower_tri row, unaligned start
+            const int64_t row_doubles = p.a_es < (int64_t)M * (M + 1) ? p.a_es : (int64_t)M * (M + 1);
+#pragma unroll
+            for (int l = 0; l < kMaxLines; l++)
+                if ((int64_t)l * 16 < row_doubles) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + l * 16));
+        }
+    }
+#endif
     double ur[M], ui[M], rr[M], ri[M];
     auto load_state = [&]() {
 #pragma unroll
