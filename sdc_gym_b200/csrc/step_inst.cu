@@ -50,7 +50,15 @@ static cudaError_t opt_in_smem(K kernel, size_t smem, std::atomic<uint64_t>& con
 // Experiments: SDCGYM_PHASE_STOPS="a,b,..." (ascending sweep counts; alone: hand over at exactly these counts whatever
 // the occupancy), SDCGYM_PHASE_LANES="a,b,..." (occupancy thresholds; alone: from the first sweep on).  An empty
 // SDCGYM_PHASE_STOPS or SDCGYM_PHASE_LANES switches the phased solve off.  At most 6 hand-overs.
+#ifndef SDCGYM_INVERSE_MINB
+#define SDCGYM_INVERSE_MINB 4  // blocks of 128 threads per SM of inverse_kernel at M = 4, 5: 128 registers (5 blocks = 96
+                               // registers spill 300 bytes at M = 5: 2.65 instead of 2.47 ms per 2^22-env strictly_lower_tri step)
+#endif
 struct PhasePlan {
+    // first pass as two launches (inverse_kernel, then the first sweeps with the inverse reloaded): measured faster than
+    // the fused first pass wherever the phased solve pays at all (2^22 envs, strictly_lower_tri, M = 3 ... 7: 0.87 /
+    // 1.36 / 2.47 / 3.70 / 5.85 ms against 0.97 / 1.49 / 2.72 / 4.10 / 8.44 ms); SDCGYM_PHASE_SPLIT=0: fused first pass
+    bool split = getenv("SDCGYM_PHASE_SPLIT") ? atoi(getenv("SDCGYM_PHASE_SPLIT")) != 0 : true;
     // one hand-over: every further pass ends with a tail of a few warps that run up to 45 dependent sweeps (>= 60 us);
     // 2^22 envs, M = 3 / 5 / 7: strictly_lower_tri 1.41 / 1.54 / 1.51 x, lower_tri 0.92 / 0.95 / 0.97 x the single launch
     int n = 1;
@@ -104,7 +112,21 @@ static cudaError_t launch_phased_dense(const StepParams<kM>& p0, const PhasePlan
     p.cont_list = lists;
     p.cont_count = counts;
     const unsigned blocks = (unsigned)((p.N + block - 1) / block);
-    first<<<blocks, block, smem, s>>>(p, nullptr, nullptr);
+    if (plan.split) {
+        // first pass in two launches: every inverse into the work planes (few registers, many warps), then the
+        // first sweeps with the inverse reloaded
+        constexpr int iminb = (kM <= 3) ? 8 : ((kM <= 5) ? SDCGYM_INVERSE_MINB : 2);
+        inverse_kernel<kM, V, iminb><<<(unsigned)((p.N + kBlock - 1) / kBlock), kBlock, 0, s>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        auto sweeps = step_phase_kernel<kM, V, hold, minb, block, 4>;
+        static std::atomic<uint64_t> conf4{0};
+        e = opt_in_smem(sweeps, smem, conf4);
+        if (e != cudaSuccess) return e;
+        sweeps<<<blocks, block, smem, s>>>(p, nullptr, nullptr);
+    } else {
+        first<<<blocks, block, smem, s>>>(p, nullptr, nullptr);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // the list lengths live on the device: every later pass is launched with one block per `block` envs of the whole

@@ -483,8 +483,28 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
             const cplx d = qd_entry(r, c, act_index(r, c));
             return f32_qd ? cmul_np_f32(cplx{zr, zi}, d) : cmul_np(cplx{zr, zi}, d);
         };
-        if constexpr (PHASE == 2) {
-            // resumed env: the inverse the first pass computed (same bits)
+        if constexpr (PHASE == 3) {
+            // inverse only (split first pass): P -> exact inverse -> work planes, nothing else; no Pinv array, the
+            // entries leave as they are produced
+            static_assert(M <= kRegInvMaxM, "the split first pass is for the register-resident inverse");
+            RegMatrix<M> A;
+#pragma unroll
+            for (int r = 0; r < M; r++)
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    const cplx zq = zq_entry(r, c);
+                    A.R(r, c) = dsub((r == c) ? 1.0 : 0.0, zq.re);
+                    A.I(r, c) = dsub(0.0, zq.im);
+                }
+            cinv_exact_reg_cols<M, V>(A, [&](int r, int c, double re, double im) {
+                if (valid) {
+                    p.pinv_scratch[(2 * (r * M + c)) * ld + i] = re;
+                    p.pinv_scratch[(2 * (r * M + c) + 1) * ld + i] = im;
+                }
+            });
+            return;
+        } else if constexpr (PHASE == 2 || PHASE == 4) {
+            // resumed env (2) / first sweeps after the inverse-only kernel (4): the inverse computed earlier (same bits)
 #pragma unroll
             for (int k = 0; k < M * M; k++) {
                 Pr[(DENSE && !PS) ? k : 0] = p.pinv_scratch[(2 * k) * ld + i];
@@ -844,15 +864,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
 // phased full solve of dense Q_delta (step_one PHASE): PHASE 1 = all envs, one per thread; PHASE 2 = the envs of
 // `list[0 .. *count)` (a fixed grid strides over the list, whose length only the device knows; threads past the end
 // run a clamped env that never sweeps and stores nothing)
+// (PHASE 4 = the first sweeps of all envs after inverse_kernel has left every inverse in the work planes)
 template <int M, int V, int HOLD, int MINB, int BLOCK, int PHASE>
 __global__ void __launch_bounds__(BLOCK, MINB) step_phase_kernel(const __grid_constant__ StepParams<M> p,
                                                                  const int32_t* __restrict__ list,
                                                                  const int32_t* __restrict__ count) {
-    static_assert(PHASE == 1 || PHASE == 2, "");
-    const int64_t n = (PHASE == 1) ? p.N : (int64_t)count[0];
+    static_assert(PHASE == 1 || PHASE == 2 || PHASE == 4, "");
+    const int64_t n = (PHASE != 2) ? p.N : (int64_t)count[0];
     for (int64_t base = (int64_t)blockIdx.x * BLOCK; base < n; base += (int64_t)gridDim.x * BLOCK) {
         const int64_t t = base + threadIdx.x;
-        const int64_t idx = (PHASE == 1) ? t : ((t < n) ? (int64_t)list[t] : p.N);
+        const int64_t idx = (PHASE != 2) ? t : ((t < n) ? (int64_t)list[t] : p.N);
         if constexpr (HOLD == 7) {
             extern __shared__ double2 pside_smem[];
             step_one<M, SDCGYM_ENV_FULL, V, true, HOLD, NoAfterLoads, PHASE>(p, idx, nullptr, 1, reinterpret_cast<cplx*>(pside_smem) + threadIdx.x, BLOCK);
@@ -863,6 +884,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_phase_kernel(const __grid_co
             step_one<M, SDCGYM_ENV_FULL, V, true, HOLD, NoAfterLoads, PHASE>(p, idx);
         }
     }
+}
+
+// split first pass, part one: the exact inverse of every env's P into the work planes.  Only the LU factors and one
+// column are live (no Pinv array, no state, no C): fewer registers, more warps per SM and a third of the code of
+// the full first pass - the inverse is bound by latency and instruction fetch, not by the FP64 pipe
+template <int M, int V, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) inverse_kernel(const __grid_constant__ StepParams<M> p) {
+    step_one<M, SDCGYM_ENV_FULL, V, true, 0, NoAfterLoads, 3>(p, (int64_t)blockIdx.x * kBlock + threadIdx.x);
 }
 
 template <int M, int HOLD, int BLOCK = kBlock>

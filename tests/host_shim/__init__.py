@@ -47,7 +47,7 @@ def shim():
         L.shim_step_hold9.argtypes = L.shim_step.argtypes
         L.shim_spectral_radius.argtypes = [ctypes.POINTER(_lib.RhoDesc), ctypes.c_int64, vp, vp, vp]
         L.shim_step_certified.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int]
-        L.shim_step_phased.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int]
+        L.shim_step_phased.argtypes = L.shim_step.argtypes + [vp, ctypes.c_int, ctypes.c_int]
         _shim = L
     return _shim
 
@@ -109,6 +109,7 @@ class ShimBatch:
         self.phase_count = np.full(_lib.PHASE_COUNTERS, -1, np.int32)
         self.phase_pinv = np.full((2 * M * M, ld), np.nan)
         self.phase_stops = (6, 16)
+        self.phase_split = True  # inverse-only pass first (the library's default)
 
     def _state(self):
         st = _lib.State()
@@ -165,7 +166,7 @@ class ShimBatch:
         elif self.entry == "shim_step_phased":
             stops = np.asarray(self.phase_stops, np.int32)
             rc = shim().shim_step_phased(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io),
-                                         stops.ctypes.data, len(stops))
+                                         stops.ctypes.data, len(stops), int(self.phase_split))
         else:
             rc = getattr(shim(), self.entry)(ctypes.byref(self.d), ctypes.byref(self._state()), ctypes.byref(io))
         assert rc == 0

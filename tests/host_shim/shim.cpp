@@ -80,7 +80,7 @@ static int step_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym
 // "threads" of every pass run one after the other; needs sdcgym_state.phase_*
 template <int M>
 static int step_phased_m(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io, const int* stops,
-                         int nstops) {
+                         int nstops, int split) {
     if constexpr (M <= 7) {
         StepParams<M> p;
         fill_params<M>(p, d, st);
@@ -96,9 +96,20 @@ static int step_phased_m(const sdcgym_env_desc* d, const sdcgym_state* st, const
         p.it_stop = stops[0];
         p.min_lanes = 33;  // at the sweep count, whatever the occupancy (the host build has no warps)
         p.cont_count = counts;
-        for (int64_t i = 0; i < nthreads; i++) {
-            if (d->blas_variant == 0) step_one<M, 0, 0, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
-            else step_one<M, 0, 1, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
+        if (split) {  // inverse_kernel, then the first sweeps with the inverse reloaded
+            for (int64_t i = 0; i < nthreads; i++) {
+                if (d->blas_variant == 0) step_one<M, 0, 0, true, 0, NoAfterLoads, 3>(p, i);
+                else step_one<M, 0, 1, true, 0, NoAfterLoads, 3>(p, i);
+            }
+            for (int64_t i = 0; i < nthreads; i++) {
+                if (d->blas_variant == 0) step_one<M, 0, 0, true, HS, NoAfterLoads, 4>(p, i, side, 3, pside, 3);
+                else step_one<M, 0, 1, true, HS, NoAfterLoads, 4>(p, i, side, 3, pside, 3);
+            }
+        } else {
+            for (int64_t i = 0; i < nthreads; i++) {
+                if (d->blas_variant == 0) step_one<M, 0, 0, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
+                else step_one<M, 0, 1, true, HS, NoAfterLoads, 1>(p, i, side, 3, pside, 3);
+            }
         }
         for (int j = 1; j <= nstops; j++) {
             if (stops[j - 1] >= p.max_iters) break;
@@ -119,15 +130,15 @@ static int step_phased_m(const sdcgym_env_desc* d, const sdcgym_state* st, const
     return -2;
 }
 extern "C" int shim_step_phased(const sdcgym_env_desc* d, const sdcgym_state* st, const sdcgym_step_io* io,
-                                const int* stops, int nstops) {
+                                const int* stops, int nstops, int split) {
     if (d->env_kind != SDCGYM_ENV_FULL) return -2;
     switch (d->M) {
-    case 2: return step_phased_m<2>(d, st, io, stops, nstops);
-    case 3: return step_phased_m<3>(d, st, io, stops, nstops);
-    case 4: return step_phased_m<4>(d, st, io, stops, nstops);
-    case 5: return step_phased_m<5>(d, st, io, stops, nstops);
-    case 6: return step_phased_m<6>(d, st, io, stops, nstops);
-    case 7: return step_phased_m<7>(d, st, io, stops, nstops);
+    case 2: return step_phased_m<2>(d, st, io, stops, nstops, split);
+    case 3: return step_phased_m<3>(d, st, io, stops, nstops, split);
+    case 4: return step_phased_m<4>(d, st, io, stops, nstops, split);
+    case 5: return step_phased_m<5>(d, st, io, stops, nstops, split);
+    case 6: return step_phased_m<6>(d, st, io, stops, nstops, split);
+    case 7: return step_phased_m<7>(d, st, io, stops, nstops, split);
     }
     return -2;
 }

@@ -180,7 +180,7 @@ for k in oa:
 assert torch.equal(a.S.view(torch.int64), b.S.view(torch.int64))
 c = b.phase_count.cpu().numpy(); nit = oa["niter"].cpu().numpy()
 import os
-if "SDCGYM_PHASE_LANES" not in os.environ:  # fixed sweep counts only: the list lengths are known
+if "SDCGYM_PHASE_LANES" not in os.environ and "SDCGYM_PHASE_STOPS" in os.environ:  # fixed sweep counts only: the list lengths are known
     stops = [int(x) for x in os.environ["SDCGYM_PHASE_STOPS"].split(",")]
     assert [int(x) for x in c[:len(stops)]] == [int((nit > s).sum()) for s in stops], (c, stops)
 else:
@@ -192,9 +192,10 @@ print("ok")
 @pytest.mark.parametrize("plan", [dict(SDCGYM_PHASE_STOPS="1"), dict(SDCGYM_PHASE_STOPS="2,3,4,5,49"),
                                   dict(SDCGYM_PHASE_STOPS="10,20,30,40,45,49"), dict(SDCGYM_PHASE_STOPS="50"),
                                   dict(SDCGYM_PHASE_LANES="32"), dict(SDCGYM_PHASE_LANES="8,8,8,8,8,8"),
-                                  dict(SDCGYM_PHASE_LANES="28,20,12"), dict(SDCGYM_PHASE_STOPS="4,12", SDCGYM_PHASE_LANES="16,16")])
+                                  dict(SDCGYM_PHASE_LANES="28,20,12"), dict(SDCGYM_PHASE_STOPS="4,12", SDCGYM_PHASE_LANES="16,16"),
+                                  dict(SDCGYM_PHASE_SPLIT="0"), dict(SDCGYM_PHASE_SPLIT="0", SDCGYM_PHASE_STOPS="3,9")])
 def test_other_hand_over_rules(plan):
-    env = {k: v for k, v in os.environ.items() if k not in ("SDCGYM_PHASE_STOPS", "SDCGYM_PHASE_LANES")}
+    env = {k: v for k, v in os.environ.items() if k not in ("SDCGYM_PHASE_STOPS", "SDCGYM_PHASE_LANES", "SDCGYM_PHASE_SPLIT")}
     env.update(plan)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _OTHER_STOPS], cwd=root, env=env, capture_output=True, text=True, timeout=600)

@@ -17,20 +17,22 @@ def _bits(a):
     return a.view(np.int64) if a.dtype == np.float64 else a
 
 
-def _batches(M, n, stops, **kw):
+def _batches(M, n, stops, split=True, **kw):
     d = host_shim.make_desc("sdc-v0", M, seed=11, **kw)
     a = host_shim.ShimBatch(d, n)
     b = host_shim.ShimBatch(d, n, entry="shim_step_phased")
     b.phase_stops = stops
+    b.phase_split = split  # True: inverse-only pass + first sweeps with the inverse reloaded; False: fused first pass
     return a, b
 
 
 @pytest.mark.parametrize("M", [2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("prec_type", ["lower_tri", "strictly_lower_tri"])
 @pytest.mark.parametrize("stops", [(6, 16), (1,), (2, 3, 5, 9, 30, 49)])
-def test_phased_passes_equal_the_single_pass(M, prec_type, stops):
+@pytest.mark.parametrize("split", [True, False])
+def test_phased_passes_equal_the_single_pass(M, prec_type, stops, split):
     n = 150 if M <= 5 else 70  # ragged against the 128-thread blocks the shim emulates
-    a, b = _batches(M, n, stops, prec_type=prec_type, do_scale=False, autoreset=True, strategy="residual_change")
+    a, b = _batches(M, n, stops, split, prec_type=prec_type, do_scale=False, autoreset=True, strategy="residual_change")
     rng = np.random.default_rng(M)
     a.reset()
     b.reset()
@@ -68,9 +70,10 @@ def test_phased_passes_against_the_oracle():
 
 @pytest.mark.parametrize("kw", [dict(prec="LU"), dict(prec_type="lower_diag"), dict(prec_type="lower_tri", cplx=True, do_scale=False),
                                 dict(prec_type="lower_tri", variant=1), dict(prec_type="lower_tri", use_doubles=False)])
-def test_phased_passes_other_configurations(kw):
+@pytest.mark.parametrize("split", [True, False])
+def test_phased_passes_other_configurations(kw, split):
     M, n = 4, 140
-    a, b = _batches(M, n, (3, 8), autoreset=True, **kw)
+    a, b = _batches(M, n, (3, 8), split, autoreset=True, **kw)
     rng = np.random.default_rng(7)
     a.reset()
     b.reset()
