@@ -145,6 +145,9 @@ static cudaError_t launch_phased_dense(const StepParams<kM>& p0, const PhasePlan
     return cudaSuccess;
 }
 
+#ifndef SDCGYM_TMEM_MINB_SMALL
+#define SDCGYM_TMEM_MINB_SMALL 5  // CTAs per SM of step_tmem_kernel at M <= 3 (96 registers; M = 4: 5 CTAs 0.563, 4 CTAs 0.550 ms)
+#endif
 template <int KIND, int V, bool DENSE>
 static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
     if constexpr (DENSE && KIND == SDCGYM_ENV_FULL && kM < kTeamMinM) {
@@ -209,6 +212,17 @@ static cudaError_t launch_step(const StepParams<kM>& p, cudaStream_t s) {
             if (q.term) q.term += done;
             q.env_offset += done;
             return launch_step<KIND, V, DENSE>(q, s);
+        }
+    }
+    if constexpr (!DENSE && !kStep && kM <= 5) {
+        // C of every env in tensor memory (step_tmem_kernel) instead of registers (M <= 4) / shared memory (M = 5).
+        // Measured per 2^20-env step (tools/bench_headline.py): M = 2 0.255 -> 0.255, M = 3 0.368 -> 0.350, M = 4
+        // 0.597 -> 0.550, M = 5 0.745 -> 0.755 ms: the default for M = 3, 4.  SDCGYM_TMEM=0 / 1: never / whenever it fits.
+        static const int tmem_env = getenv("SDCGYM_TMEM") ? atoi(getenv("SDCGYM_TMEM")) : -1;
+        const bool use_tmem = tmem_env < 0 ? (kM == 3 || kM == 4) : tmem_env != 0;
+        if (use_tmem && p.old_states == nullptr) {
+            step_tmem_kernel<kM, V, (kM <= 3) ? SDCGYM_TMEM_MINB_SMALL : 4><<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+            return cudaGetLastError();
         }
     }
     constexpr int hold = DENSE ? kHoldDense : (kStep ? HoldPolicy<kM>::step : kHoldDiag);

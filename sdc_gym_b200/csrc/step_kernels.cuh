@@ -306,6 +306,64 @@ SDCGYM_HD cplx ld_pair(const cplx* p) {
 #endif
 }
 
+// ---- tensor memory (TMEM) as a per-thread scratch store (HOLD 10) ----
+// TMEM is 128 lanes x 512 32-bit columns per SM, read and written with tcgen05.ld / tcgen05.st: warp w of a CTA reaches
+// lanes 32 (w % 4) ... + 31, thread t of the warp its own lane.  A thread's (re, im) pair is four consecutive columns.
+// All of these are .sync.aligned: the whole warp must execute them together.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void tmem_st_pair(uint32_t taddr, double re, double im) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__double2loint(re)),
+                 "r"(__double2hiint(re)), "r"(__double2loint(im)), "r"(__double2hiint(im))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_pair(uint32_t taddr, int (&w)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, int* w) {  // N = 4, 8 or 16 consecutive columns
+    static_assert(N == 4 || N == 8 || N == 16, "");
+    if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                     : "r"(taddr)
+                     : "memory");
+    } else if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "r"(taddr)
+                     : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+              "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(taddr)
+            : "memory");
+    }
+}
+// one row of C (M pairs = 4 M columns) in as few loads as the power-of-two shapes allow
+template <int M>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, int (&w)[4 * M]) {
+    constexpr int n = 4 * M;
+    int done = 0;
+    if constexpr (n >= 16) {
+        tmem_ld_cols<16>(taddr, w);
+        done = 16;
+    }
+    if constexpr ((n & 15) >= 8) {
+        tmem_ld_cols<8>(taddr + (n & ~15), w + (n & ~15));
+        done += 8;
+    }
+    if constexpr ((n & 7) >= 4) tmem_ld_cols<4>(taddr + (n & ~7), w + (n & ~7));
+    (void)done;
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#endif
+
 struct NoAfterLoads {
     SDCGYM_HD void operator()() const {}
 };
@@ -325,7 +383,7 @@ struct NoAfterLoads {
 template <int M, int KIND, int V, bool DENSE, int HOLD, class AfterLoads = NoAfterLoads, int PHASE = 0>
 SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side = nullptr, const int side_stride = 1,
                         cplx* pside = nullptr, const int pstride = 1, const StepInputs* in = nullptr,
-                        AfterLoads after_loads = AfterLoads()) {
+                        AfterLoads after_loads = AfterLoads(), const uint32_t taddr = 0) {
     const bool valid = tid < p.N;
     const int64_t i = valid ? tid : p.N - 1;
     const int64_t ld = p.ld;
@@ -586,6 +644,10 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
     constexpr bool CS = (HOLD == 4 || HOLD == 8);  // C lives in the (double) side store
     constexpr int NCR = (HOLD >= 1 && HOLD <= 3) ? M * M : 1, NCI = (HOLD == 2) ? M * M : 1;
     double Cr[NCR], Ci[NCI];
+    static_assert(HOLD != 10 || (!DENSE && KIND == SDCGYM_ENV_FULL && 4 * M * M <= 128), "HOLD 10: C in tensor memory");
+#ifdef __CUDA_ARCH__
+    if constexpr (HOLD == 10) __syncwarp();  // (the reciprocals above have divergent slow paths)
+#endif
     if (HOLD >= 1 && HOLD != 9) {
 #pragma unroll
         for (int r = 0; r < M; r++)
@@ -598,9 +660,15 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
                 if (HOLD == 2) Ci[(HOLD == 2) ? r * M + c : 0] = -dmul(zi, q);
                 if (HOLD == 3 || CS) side[(r * M + c) * side_stride] = -dmul(zi, q);
                 if (HOLD == 5 || HOLD == 7) pside[(r * M + c) * pstride] = cplx{crv, -dmul(zi, q)};
+#ifdef __CUDA_ARCH__
+                if constexpr (HOLD == 10) tmem_st_pair(taddr + 4 * (r * M + c), crv, -dmul(zi, q));
+#endif
                 if (HOLD == 6) side[(r * M + c) * side_stride] = crv;
             }
     }
+#ifdef __CUDA_ARCH__
+    if constexpr (HOLD == 10) tmem_wait_st();
+#endif
 
 
     if (DENSE) load_state();
@@ -611,7 +679,9 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         norm_old_scaled = scaled_inf_norm<M>(rr, ri, p.norm_factor);
 
     // one sweep: u += Pinv @ r ; r = u0 - C @ u      (sdc_env.py:229-231 / :516-519)
-    auto sweep = [&]() {
+    // (`commit`: HOLD 10 runs the sweep with the whole warp - its tensor-memory loads are warp-collective - and keeps
+    //  the new state only in the lanes that are still iterating)
+    auto sweep = [&](const bool commit = true) {
         // when C is not register resident its entries are re-derived from z and the constant-bank Q on every
         // sweep; the empty asm keeps the compiler from hoisting those products back out of the loop (which
         // would turn them into spills).
@@ -649,14 +719,31 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         }
 #pragma unroll
         for (int m = 0; m < M; m++) {
-            ur[m] = dadd(ur[m], dr[m]);
-            ui[m] = dadd(ui[m], di[m]);
+            // HOLD 10: lanes that are done keep u (and therefore get the very same r back from the row products below)
+            if (HOLD != 10 || commit) {
+                ur[m] = dadd(ur[m], dr[m]);
+                ui[m] = dadd(ui[m], di[m]);
+            }
         }
 #pragma unroll
         for (int m = 0; m < M; m++) {
             double cr[M], ci[M], yr, yi;
+#ifdef __CUDA_ARCH__
+            if constexpr (HOLD == 10) {
+                // row m of C from tensor memory: M warp-collective loads of one (re, im) pair per lane, one wait
+                int w[4 * M];
+                tmem_ld_row<M>(taddr + 4 * (m * M), w);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < M; c++) {
+                    cr[c] = __hiloint2double(w[4 * c + 1], w[4 * c]);
+                    ci[c] = __hiloint2double(w[4 * c + 3], w[4 * c + 2]);
+                }
+            }
+#endif
 #pragma unroll
             for (int c = 0; c < M; c++) {
+                if (HOLD == 10) break;
                 double q = p.Q[m * M + c];
                 cplx t7{0.0, 0.0};
                 if (HOLD == 7) t7 = ld_pair(&pside[(m * M + c) * pstride]);  // HOLD 7: C as (re, im) pairs, one LDS.128
@@ -689,9 +776,15 @@ SDCGYM_HD void step_one(const StepParams<M>& p, const int64_t tid, double* side 
         const SqBand sc = make_sqband(p.restol), se = make_sqband(thr);
         bool act = p.max_iters > 0 && (PHASE == 0 || valid);
         while (SDCGYM_WARP_ANY(act)) {
+            if constexpr (HOLD == 10) {
+#ifdef __CUDA_ARCH__
+                __syncwarp();
+#endif
+                sweep(act);  // warp-collective; commits where act
+            }
             if (act) {
                 it++;
-                sweep();
+                if constexpr (HOLD != 10) sweep();
                 // decide `err` (nr is NaN/Inf or nr > thr) and `conv` (nr < restol) without forming nr:
                 // stage 1 on the integer pipe, stage 2 on squared magnitudes, exact norm as a last resort.
                 const int H = absmax_hi<M>(rr, ri);
@@ -859,6 +952,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) step_kernel(const __grid_constant
     } else {
         step_one<M, KIND, V, DENSE, HOLD>(p, (int64_t)blockIdx.x * BLOCK + threadIdx.x);
     }
+}
+
+// full solve, diagonal Q_delta, the system matrix C of every env in TENSOR MEMORY (HOLD 10).  The shipped kernel keeps C
+// in shared memory and is co-limited by the FP64 pipe (77 %) and the shared-memory pipe (81 %: 25 LDS.128 per sweep
+// and thread); tensor memory has its own path to the register file.  One CTA = 128 threads = the 128 TMEM lanes, a
+// thread's C = 4 M^2 32-bit columns of its lane (M = 5: 100 of an allocation of 128; four CTAs fill the SM's 512).
+template <int M, int V, int MINB>
+__global__ void __launch_bounds__(128, MINB) step_tmem_kernel(const __grid_constant__ StepParams<M> p) {
+    constexpr uint32_t kCols = (4 * M * M <= 32) ? 32u : ((4 * M * M <= 64) ? 64u : 128u);
+    static_assert(4 * M * M <= 128, "C does not fit a quarter of the tensor memory");
+    __shared__ uint32_t tbase;
+    const uint32_t warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tbase)),
+                     "r"(kCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tbase + ((warp * 32u) << 16);
+    step_one<M, SDCGYM_ENV_FULL, V, false, 10>(p, (int64_t)blockIdx.x * 128 + threadIdx.x, nullptr, 1, nullptr, 1, nullptr,
+                                               NoAfterLoads(), taddr);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // (every thread comes back from step_one: its early exits are returns of the inlined body)
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(kCols) : "memory");
 }
 
 // phased full solve of dense Q_delta (step_one PHASE): PHASE 1 = all envs, one per thread; PHASE 2 = the envs of

@@ -247,3 +247,40 @@ def test_tiny_batches_when_asked_for(n):
     rng = np.random.default_rng(n)
     for s in range(3):
         _same_step(a, b, rng.uniform(0, 0.3, (n, num_actions(5, "strictly_lower_tri"))))
+
+
+_TMEM_CHECK = r"""
+import numpy as np, torch, sys
+import sdc_gym_b200
+from oracle import exact
+from sdc_gym_b200.collocation import collocation_matrix
+M, n = int(sys.argv[1]), 20000 + 11
+Q = collocation_matrix(M)
+rng = np.random.default_rng(M)
+lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
+act = rng.uniform(-1, 1, (n, M))
+env = sdc_gym_b200.make("sdc-v0", num_envs=n, M=M, dt=1.0, restol=1e-10, autoreset=False,
+                        lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0])
+env.reset(lam=lam)
+_, rew, done, infos = env.step(act)
+u, r = exact.reset(Q, 1.0, lam)
+niter = np.zeros(n, np.int32)
+out = exact.step("sdc-v0", Q, 1.0, lam, u, r, niter, r.copy(), act)
+snap = env._snapshot()
+assert np.array_equal(snap["obs"][:, 0].view(np.int64), u.view(np.int64))
+assert np.array_equal(snap["obs"][:, 1].view(np.int64), r.view(np.int64))
+assert np.array_equal(infos.niter, niter)
+assert np.array_equal(np.asarray(infos.residual).view(np.int64), out["resnorm"].view(np.int64))
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("M", [2, 3, 4, 5])
+def test_system_matrix_in_tensor_memory_variant_equals_oracle(M):
+    """SDCGYM_TMEM=1 (experiment switch, csrc/step_kernels.cuh step_tmem_kernel): the diagonal full solve with every
+    env's C in tensor memory (tcgen05.alloc / st / ld) instead of shared memory - a different store for the same
+    numbers, so the oracle comparison is bit for bit.  Own process (the switch is read once) with a time limit."""
+    env = dict(os.environ, SDCGYM_TMEM="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _TMEM_CHECK, str(M)], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
