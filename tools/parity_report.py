@@ -30,6 +30,7 @@ def _oracle_chunk(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1 << 20)
+    ap.add_argument("--only-round2", action="store_true", help="only the cases added in round 2")
     args = ap.parse_args()
     import torch
     import sdc_gym_b200
@@ -42,8 +43,19 @@ def main():
              ("sdc-v0", 5, "diag", "LU", "-", args.envs // 4, 1), ("sdc-v0", 5, "lower_tri", None, "small", args.envs // 4, 1),
              ("sdc-v0", 7, "strictly_lower_tri", None, "small", args.envs // 8, 1),
              ("sdc-v0", 9, "lower_tri", None, "small", args.envs // 16, 1),
-             ("sdc-v1", 5, "diag", None, "good", args.envs // 4, 8)]
-    for kind, M, pt, prec, mode, n, steps in cases:
+             ("sdc-v1", 5, "diag", None, "good", args.envs // 4, 8),
+             # round 2: the phased dense solve (forced: phased=True) on the config-3 workload, and the diagonal full
+             # solve with C in tensor memory (the default at M = 3, 4)
+             ("sdc-v0", 5, "strictly_lower_tri", None, "cfg3", args.envs, 1, True),
+             ("sdc-v0", 5, "lower_tri", None, "cfg3", args.envs // 2, 1, True),
+             ("sdc-v0", 7, "strictly_lower_tri", None, "cfg3", args.envs // 4, 1, True),
+             ("sdc-v0", 3, "lower_tri", None, "cfg3", args.envs // 2, 1, True),
+             ("sdc-v0", 4, "diag", None, "uniform", args.envs, 1), ("sdc-v0", 3, "diag", None, "uniform", args.envs, 1)]
+    if args.only_round2:
+        cases = cases[7:]
+    for case in cases:
+        kind, M, pt, prec, mode, n, steps = case[:7]
+        phased = case[7] if len(case) > 7 else None
         lam = rng.uniform(-100, 0, n) + 1j * rng.uniform(-10, 0, n)
         A = num_actions(M, pt)
         if prec:
@@ -53,10 +65,12 @@ def main():
         elif mode == "good":
             x = np.diag(fixed_preconditioner("min", M))
             act = 2 * (x[None, None] + rng.uniform(-0.03, 0.03, (steps, n, M))) - 1
+        elif mode == "cfg3":
+            act = rng.uniform(0, 0.3, (steps, n, A))
         else:
             act = rng.uniform(0, 0.12, (steps, n, A))
         env = sdc_gym_b200.make(kind, num_envs=n, M=M, dt=1.0, restol=1e-10, prec=prec, prec_type=pt,
-                                do_scale=(pt == "diag"), blas_variant=_lib.BLAS_SKYLAKEX, autoreset=False,
+                                do_scale=(pt == "diag"), blas_variant=_lib.BLAS_SKYLAKEX, autoreset=False, phased=phased,
                                 lambda_real_interval=[-100, 0], lambda_imag_interval=[-10, 0])
         env.reset(lam=lam)
         t0 = time.perf_counter()
@@ -77,6 +91,8 @@ def main():
         conv_or_done = ((g["flags"] & 2) != 0) if kind == "sdc-v0" else ((g["flags"] & 1) != 0)
         print(json.dumps({
             "kind": kind, "M": M, "prec_type": pt if not prec else prec, "actions": mode, "envs": n, "steps": steps,
+            "launch": ("phased" if getattr(env, "phased", False) else "single"),
+            "handed_over": (int(env.phase_count[0]) if getattr(env, "phased", False) else None),
             "mismatch_niter": int(np.sum(g["niter"] != nit)), "mismatch_done_or_converged": int(np.sum(conv_or_done != done)),
             "mismatch_err": int(np.sum(((g["flags"] & 4) != 0) != err)), "mismatch_residual_norm": eq(g["res"], res),
             "mismatch_u_components": eq(g["u"].real, u.real) + eq(g["u"].imag, u.imag),
